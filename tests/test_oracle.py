@@ -1,0 +1,131 @@
+"""CPU: the oracle restatement against the golden vectors produced by the unmodified reference, plus the analytic
+known answers of SURVEY.md section 4.  This is what pins the oracle (it is the checker for every -m gpu test)."""
+import numpy as np
+import pytest
+
+from tests.conftest import relerr
+from oracle import sem_oracle as so
+from tests.golden.make_golden_cases import CD_CASES, MESHES, NS_CASES
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16])
+def test_gll_tables_match_reference(golden, P):
+    g = golden("gll")
+    x, w, _ = so.gll(P)
+    assert np.array_equal(x, g[f"x{P}"]) and np.array_equal(w, g[f"w{P}"])
+    assert np.array_equal(so.diff_matrix(P), g[f"D{P}"])
+    assert np.array_equal(so.stiff_1d(P), g[f"K{P}"])
+    assert np.array_equal(so.grad_1d(P), g[f"G{P}"])
+    assert np.allclose(so.eval_matrix(P, np.linspace(-1, 1, 7)), g[f"S{P}"], rtol=0, atol=1e-13)
+
+
+def test_gll_known_answers():
+    x, w, _ = so.gll(4)
+    assert np.allclose(x, [-1, -np.sqrt(3 / 7), 0, np.sqrt(3 / 7), 1], atol=1e-15)
+    assert np.allclose(w, [1 / 10, 49 / 90, 32 / 45, 49 / 90, 1 / 10], atol=1e-15)
+    for P in range(1, 13):
+        x, w, _ = so.gll(P)
+        D = so.diff_matrix(P)
+        assert abs(w.sum() - 2) < 1e-14
+        assert np.max(np.abs(D.sum(axis=1))) < 1e-12
+        assert np.max(np.abs(D @ x**P - P * x**(P - 1))) < 1e-12
+        K = so.stiff_1d(P)
+        assert np.max(np.abs(K - K.T)) < 1e-13 and np.max(np.abs(K @ np.ones(P + 1))) < 1e-12
+
+
+@pytest.mark.parametrize("tag,P,nx,ny,Lx,Ly", MESHES)
+def test_operators_match_reference(golden, tag, P, nx, ny, Lx, Ly):
+    g = golden("operators")
+    x = g[f"{tag}/x"]
+    M, K, Gx, Gy = so.global_operators(P, nx, ny, Lx / nx, Ly / ny)
+    assert relerr(M, g[f"{tag}/Mdiag"]) < 1e-15
+    assert relerr(K @ x, g[f"{tag}/Kx"]) < 1e-13
+    assert relerr(Gx @ x, g[f"{tag}/Gxx"]) < 1e-13
+    assert relerr(Gy @ x, g[f"{tag}/Gyx"]) < 1e-13
+    assert abs(M.sum() - Lx * Ly) < 1e-13 * Lx * Ly
+    assert np.array_equal(so.global_nodes(P, nx, ny, Lx / nx, Ly / ny), g[f"{tag}/points"])
+    assert relerr(so.assemble_vector(g[f"{tag}/A_e"]), g[f"{tag}/assembled"]) < 1e-15
+    assert np.array_equal(so.scatter(x, P, nx, ny), g[f"{tag}/scattered"])
+    val = so.interpolate(x, P, nx, ny, Lx / nx, Ly / ny, (g[f"{tag}/xp"], g[f"{tag}/yp"]))
+    assert relerr(val, g[f"{tag}/interp"]) < 1e-13
+
+
+def test_global_index_errors():
+    with pytest.raises(ValueError):
+        so.global_index(4, 2, 2, 2, 0, 0, 0)
+    with pytest.raises(ValueError):
+        so.scatter(np.zeros(7), 2, 2, 2)
+    assert so.global_index(4, 16, 16, 3, 5, 2, 1) == 5 * 4 + 1 + 65 * (3 * 4 + 2)
+
+
+@pytest.mark.parametrize("tag,kw", CD_CASES)
+def test_cd_matches_reference(golden, tag, kw):
+    g = golden("cd")
+    cd = so.CDOracle(mtol=1e-13, **kw)
+    k = lambda s: g[f"{tag}/{s}"]
+    assert np.array_equal(cd._mask_dir, k("mask_dir"))
+    assert np.array_equal(np.nan_to_num(cd._dirichlet, nan=9e99), np.nan_to_num(k("dirichlet"), nan=9e99))
+    assert relerr(cd._get_residuals(k("T"), k("ur"), k("vr")), k("res_r")) < 1e-13
+    cd._calc_jacobians(k("T"))
+    assert relerr(cd._get_dresiduals(k("dT")), k("dres_r")) < 1e-13
+    assert relerr(cd._get_dresiduals(k("dT"), k("du"), k("dv")), k("dres_r_uv")) < 1e-13
+    assert relerr(cd._get_dresiduals(k("dT"), du=k("du")), k("dres_r_u")) < 1e-13
+    assert relerr(cd._get_residuals(k("T"), k("u"), k("v")), k("res")) < 1e-13
+    assert relerr(cd._get_dresiduals(k("dT")), k("dres")) < 1e-13
+    assert relerr(cd._get_solution(k("u"), k("v")), k("T_sol")) < 1e-9
+    assert relerr(cd._get_update(k("rhs")), k("dT_sol")) < 1e-9
+
+
+@pytest.mark.parametrize("tag,kw,solve", NS_CASES)
+def test_ns_matches_reference(golden, tag, kw, solve):
+    g = golden("ns")
+    ns = so.NSOracle(mtol=1e-13, mtol_newton=1e-13, **kw)
+    k = lambda s: g[f"{tag}/{s}"]
+    assert np.array_equal(ns._mask_bound, k("mask_bound"))
+    ru, rv, rc = ns._get_residuals(k("u"), k("v"), k("p"), k("T"))
+    assert relerr(ru, k("res_u")) < 1e-13 and relerr(rv, k("res_v")) < 1e-13 and relerr(rc, k("res_c")) < 1e-13
+    ns._calc_jacobians(k("u"), k("v"))
+    a, b, c = ns._get_dresiduals(k("du"), k("dv"), k("dp"))
+    assert relerr(a, k("dres_u")) < 1e-13 and relerr(b, k("dres_v")) < 1e-13 and relerr(c, k("dres_c")) < 1e-13
+    a, b, c = ns._get_dresiduals(k("du"), k("dv"), k("dp"), k("dT"))
+    assert relerr(a, k("dresT_u")) < 1e-13 and relerr(b, k("dresT_v")) < 1e-13 and relerr(c, k("dresT_c")) < 1e-13
+    # the assembled Jacobian matrix reproduces the JVP (it is what the oracle's direct solve factorises)
+    J = ns.jacobian_matrix()
+    jv = J @ np.hstack((k("du"), k("dv"), k("dp")))
+    assert relerr(jv, np.hstack((k("dres_u"), k("dres_v"), k("dres_c")))) < 1e-13
+    if not solve:
+        return
+    u, v, p = ns._get_solution(k("T_in"))
+    # The stored reference fields stop at the reference's own tolerance (|res| <= 1e-13 sqrt(3N)); on the 8x8 mesh
+    # its smallest singular values (~1e-5) turn that into ~6e-8 in p -- a floor of the reference, not of the oracle.
+    ptol = 2e-7 if tag == "c3" else 1e-8
+    assert relerr(u, k("u_sol")) < 1e-8 and relerr(v, k("v_sol")) < 1e-8 and relerr(p, k("p_sol")) < ptol
+    ns._get_residuals(k("u_sol"), k("v_sol"), k("p_sol"), k("T_in"))
+    ns._calc_jacobians(k("u_sol"), k("v_sol"))
+    a, b, c = ns._get_update(k("rhs_u"), k("rhs_v"), k("rhs_c"))
+    assert relerr(a, k("upd_u")) < 1e-8 and relerr(b, k("upd_v")) < 1e-8 and relerr(c, k("upd_p")) < 1e-8
+
+
+def test_readme_helmholtz_known_answer():
+    """Solvers/README.md:49-96: (lambda M + K) u = M f with f = cos(pi x/Lx) cos(pi y/Ly), homogeneous Neumann;
+    exact u = f / (lambda + pi^2 (1/Lx^2 + 1/Ly^2)).  Max error 9.5e-7 at P=4, 2x3 elements."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    Lx, Ly, lam, P, nx, ny = 2.0, 1.0, 1.0, 4, 2, 3
+    M, K, _, _ = so.global_operators(P, nx, ny, Lx / nx, Ly / ny)
+    pts = so.global_nodes(P, nx, ny, Lx / nx, Ly / ny)
+    f = np.cos(np.pi * pts[0] / Lx) * np.cos(np.pi * pts[1] / Ly)
+    u = spla.spsolve((lam * sps.diags(M) + K).tocsc(), M * f)
+    exact = f / (lam + np.pi**2 * (1 / Lx**2 + 1 / Ly**2))
+    assert np.max(np.abs(u - exact)) < 5e-5
+
+
+def test_boussinesq_fixed_point_residual(golden):
+    """The stored C3 coupled state is a root of the oracle's four residuals and reproduces de Vahl Davis (1983)."""
+    g = golden("boussinesq_c3")
+    Re, Ra, Pr = 1e3, 1e3, 0.71
+    cd = so.CDOracle(1., 1., Re * Pr, 4, 8, 8, T_W=0.5, T_E=-0.5)
+    ns = so.NSOracle(1., 1., Re, Ra / Pr, 4, 8, 8)
+    r = np.hstack((cd._get_residuals(g["T"], g["u"], g["v"]),) + ns._get_residuals(g["u"], g["v"], g["p"], g["T"]))
+    assert np.linalg.norm(r) < 1e-9 * np.sqrt(r.size)
+    assert abs(float(g["umax_RePr"]) - 3.649) < 5e-3 and abs(float(g["vmax_RePr"]) - 3.697) < 1e-2
