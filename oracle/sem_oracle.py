@@ -401,19 +401,33 @@ class NSOracle:
 
         With equal-order velocity/pressure spaces and the boundary rows of NS:155-158 the 3N x 3N Jacobian has, on
         most meshes, a one-dimensional null space (a spurious pressure mode); its left null vector ``l`` vanishes on
-        the interior momentum rows and does not depend on the linearisation point.  Found by one bordered sparse LU.
+        the interior momentum rows and does not depend on the linearisation point (cached).  Found by one sparse LU
+        of ``J^T`` with one (redundant) equation replaced by the normalisation ``l[r*] = 1``.
         """
+        if getattr(self, "_l_cache", None) is not None:
+            return self._l_cache if self._l_cache is not False else None
         n = J.shape[0]
-        rng = np.random.default_rng(12345)
-        r1, r2 = rng.standard_normal(n), rng.standard_normal(n)
-        B = sps.bmat([[J.T, sps.csr_matrix(r1[:, None])], [sps.csr_matrix(r2[None, :]), None]], format='csc')
-        rhs = np.zeros(n + 1)
-        rhs[-1] = 1.0
-        l = spla.splu(B).solve(rhs)[:n]
+        r_star = 2 * self.N + self._interior_probe()
+        JT = J.T.tolil()
+        JT[r_star, :] = 0
+        JT[r_star, r_star] = 1.0
+        rhs = np.zeros(n)
+        rhs[r_star] = 1.0
+        l = spla.splu(JT.tocsc()).solve(rhs)
         l /= np.linalg.norm(l)
         if np.linalg.norm(J.T @ l) > 1e-9 * spla.norm(J, np.inf):
+            self._l_cache = False
             return None
+        self._l_cache = l
         return l
+
+    def _interior_probe(self):
+        """Index of the mesh-interior node (ix, iy) = (1, 1) (never the pin, never on the boundary)."""
+        NY = self._N_ey * self._P + 1
+        k = NY + 1
+        if k == self._pin:
+            k += 1
+        return k
 
     def _get_update(self, dres_u, dres_v, dres_cont, du0=None, dv0=None, dp0=None):
         """Solve the linearised system  (NS:162-236).
@@ -422,9 +436,11 @@ class NSOracle:
         complement ``S`` from ``dp0`` (or 0) with the diagonal-mass preconditioner of NS:208-212 (pin row passed
         through).  ``S`` is singular but the system is consistent, and that iteration converges to the one solution
         with ``M_p (dp - dp0)`` in ``range(S)``, i.e. ``l_c . (M_p (dp - dp0)) = 0`` for the left null vector
-        ``l = (l_u, l_v, l_c)`` of the Jacobian.  The oracle computes that same solution directly: a bordered sparse
-        LU of ``[[J, l], [m^T, 0]]`` with ``m = (0, 0, M_p l_c)``.  (Checked against the reference's own converged
-        output in tests/golden/ns.npz.)  When J is regular the border is dropped.
+        ``l = (l_u, l_v, l_c)`` of the Jacobian.  The oracle computes that same solution directly: the continuity
+        equation of one interior node is redundant (``l`` is non-zero there); it is replaced by ``p[node] = 0`` to get
+        a particular solution and the right null vector from one sparse LU, and the solution is shifted along the
+        null vector until ``m . (x - x0) = 0`` with ``m = (0, 0, M_p l_c)``.  (Checked against the
+        reference's own converged output in tests/golden/ns.npz.)  When J is regular it is solved as is.
         """
         N = self.N
         J = self.jacobian_matrix()
@@ -436,9 +452,18 @@ class NSOracle:
         Mp[self._pin] = 1.0
         m = np.hstack((np.zeros(2 * N), Mp * l[2 * N:]))
         x0 = np.hstack([np.zeros(N) if a is None else a for a in (du0, dv0, dp0)])
-        B = sps.bmat([[J, sps.csr_matrix(l[:, None])], [sps.csr_matrix(m[None, :]), None]], format='csc')
-        sol = spla.splu(B).solve(np.hstack((b, m @ x0)))[:3 * N]
-        return tuple(np.split(sol, 3))
+        # regularise with a sparse row instead of the dense constraint row: p[probe] = 0 gives a particular solution
+        # x1 and the same LU yields the right null vector q (J_r q = e_r*); then shift along q onto the constraint.
+        r_star = 2 * N + self._interior_probe()
+        keep = np.ones(3 * N)
+        keep[r_star] = 0.0
+        unit = np.zeros(3 * N)
+        unit[r_star] = 1.0
+        lu = spla.splu((sps.diags(keep) @ J + sps.diags(unit)).tocsc())
+        x1 = lu.solve(b * keep)
+        q = lu.solve(unit)
+        alpha = (m @ (x1 - x0)) / (m @ q)
+        return tuple(np.split(x1 - alpha * q, 3))
 
     def _get_solution(self, T, u0=None, v0=None, p0=None, max_newton=50):
         """Newton loop, stop on the spectral norm of the 3 x N residual array <= mtol_newton sqrt(3N)  (NS:238-270)."""
