@@ -129,6 +129,8 @@ int sem_ns_solve(sem_ctx *ctx, const sem_ns_state *st, const double *rhs3, doubl
 
 /* ---- reductions used by the Python layer (deterministic two-stage sums) ---------------------------------------- */
 int sem_dot(sem_ctx *ctx, const double *x, const double *y, long long n, double *host_out, void *stream);
+/* y = a*x + b*y over n doubles (b == 0: y = a*x); the Newton update u += du of NS:265-267 / T + dT of CD:170 */
+int sem_axpby(sem_ctx *ctx, double a, const double *x, double b, double *y, long long n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,241 @@
+"""GPU Navier-Stokes solver -- same class, constructor and method signatures as the reference's
+``Solvers/NavierStokes_Solver.py`` (cited below as NS:line).  numpy in / numpy out; fields, the linearisation state
+and the Krylov basis live on the B200; every operation is a call into ``libsem_b200.so`` (no CPU fallback).
+
+Linear solve.  The reference factorises the velocity block with SuperLU and runs LGMRES on the pressure Schur
+complement with a diagonal-mass right preconditioner (NS:162-236).  Here the whole 3-field system is solved by
+right-preconditioned GMRES with the block lower-triangular preconditioner [[P_a, 0], [C, M_p]] (P_a = Jacobi on the
+velocity block, C = continuity rows, M_p = the reference's mass preconditioner).  The linearised system is singular
+but consistent on most meshes (equal-order spaces); this structure makes GMRES pick the same member of
+the solution family as the reference's Schur iteration, so pressures agree too.
+"""
+import ctypes as C
+import typing
+
+import numpy as np
+import torch
+
+from . import SEM
+from . import _lib as L
+from .device import SemDevice
+
+
+class NavierStokesSolver:
+    def __init__(self, L_x: float, L_y: float, Re: float, Gr: float, P: int, N_ex: int, N_ey: int,
+                 v_W: float = 0, v_E: float = 0, u_S: float = 0, u_N: float = 0,
+                 mtol=1e-7, mtol_newton=1e-5, iprint: list = ['NEWTON_suc', 'NEWTON_iter'],
+                 device: int = None, restart: int = None, max_newton: int = 50):
+        """Arguments as NS:11-41.  Extra, optional: ``device``, ``restart`` (Krylov basis size), ``max_newton``."""
+        self._iprint = iprint
+        self._Re = Re
+        self._Gr = Gr
+        if self._Re == 0 and self._Gr != 0:
+            raise ValueError('Cannot have Re == 0 and Gr != 0')                     # NS:46-47
+        self._Gr_over_Re = self._Gr / self._Re if self._Re != 0 else 0.
+        self._mtol = mtol
+        self._mtol_newton = mtol_newton
+        self._L_x, self._L_y = L_x, L_y
+        self._P, self._N_ex, self._N_ey = P, N_ex, N_ey
+        self._dx, self._dy = L_x / N_ex, L_y / N_ey
+        self.N = (N_ex * P + 1) * (N_ey * P + 1)
+        self._points = None
+        self._points_e = None
+        self._k = 0
+        self._max_newton = max_newton
+
+        self._dev = SemDevice(P, N_ex, N_ey, self._dx, self._dy, device=device)
+        self._lib = self._dev.lib
+        self._bc = L.sem_ns_bc(float(v_W), float(v_E), float(u_S), float(u_N))
+        d = self._dev
+        self._uv = d.zeros(2)        # advecting velocity of the last _get_residuals  (self._Sys of NS:106)
+        self._jac = d.zeros(4)       # Re G_x u, Re G_y u, Re G_x v, Re G_y v          (self._Jac_* of NS:131-136)
+        self._have_sys = False
+        self._have_jac = False
+        self._in = d.zeros(4)        # staging of (u, v, p, T) style inputs
+        self._out = d.zeros(3)
+        self._x = d.zeros(3)
+        self._restart = restart
+        self._work = None
+        self.last_iters = 0
+        self.last_resnorm = float('nan')
+        self.krylov_iters = []       # iterations of every linear solve since construction
+
+    @property
+    def points(self):
+        if self._points is None:
+            self._points = SEM.global_nodes(self._P, self._N_ex, self._N_ey, self._dx, self._dy)
+        return self._points
+
+    @property
+    def points_e(self):
+        if self._points_e is None:
+            self._points_e = SEM.element_nodes(self._P, self._N_ex, self._N_ey, self._dx, self._dy)
+        return self._points_e
+
+    # ---- internals -------------------------------------------------------------------------------------------------------
+    def _state(self):
+        st = L.sem_ns_state()
+        st.bc = self._bc
+        st.Re, st.Gr_over_Re = float(self._Re), float(self._Gr_over_Re)
+        st.u, st.v = self._uv[0].data_ptr(), self._uv[1].data_ptr()
+        if self._have_jac:
+            st.gxu, st.gyu = self._jac[0].data_ptr(), self._jac[1].data_ptr()
+            st.gxv, st.gyv = self._jac[2].data_ptr(), self._jac[3].data_ptr()
+        return st
+
+    def _residual_dev(self, u, v, p, T, out3):
+        """Device residual; also records (u, v) as the linearisation point like NS:103-106."""
+        d = self._dev
+        self._uv[0].copy_(u)
+        self._uv[1].copy_(v)
+        self._have_sys = True
+        st = self._state()
+        L.check(self._lib.sem_ns_residual(d.ctx, C.byref(st), u.data_ptr(), v.data_ptr(), p.data_ptr(), T.data_ptr(),
+                                          out3[0].data_ptr(), out3[1].data_ptr(), out3[2].data_ptr(), d.stream),
+                "sem_ns_residual")
+
+    def _jacobians_dev(self, u, v):
+        d = self._dev
+        L.check(self._lib.sem_ns_jacobians(d.ctx, float(self._Re), u.data_ptr(), v.data_ptr(),
+                                           self._jac[0].data_ptr(), self._jac[1].data_ptr(),
+                                           self._jac[2].data_ptr(), self._jac[3].data_ptr(), d.stream),
+                "sem_ns_jacobians")
+        self._have_jac = True
+
+    def _krylov(self):
+        if self._restart is None:
+            free = torch.cuda.mem_get_info(self._dev.tdev)[0]
+            cap = max(20, int(0.4 * free / (8 * 3 * self._dev.vec_len)) - 3)
+            self._restart = int(min(4000, max(50, self.N), cap))
+        need = self._lib.sem_ns_work_len(self._dev.ctx, self._restart)
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty(need, dtype=torch.float64, device=self._dev.tdev)
+        kr = L.sem_krylov()
+        kr.atol = float(self._mtol * np.sqrt(self.N))            # NS:223
+        kr.restart = self._restart
+        kr.max_iters = max(2000, 10 * self._restart)
+        kr.precond = 1
+        kr.verbose = 2 if 'LGMRES_iter' in self._iprint else 0
+        return kr
+
+    def _solve_dev(self, rhs3, x3):
+        if not (self._have_sys and self._have_jac):
+            raise RuntimeError('NavierStokes: _get_residuals and _calc_jacobians must precede a linear solve')
+        kr = self._krylov()
+        st = self._state()
+        code = L.check(self._lib.sem_ns_solve(self._dev.ctx, C.byref(st), rhs3.data_ptr(), x3.data_ptr(),
+                                              C.byref(kr), self._work.data_ptr(), self._work.numel(),
+                                              self._dev.stream), "sem_ns_solve")
+        self.last_iters, self.last_resnorm = kr.iters, kr.resnorm
+        self.krylov_iters.append(kr.iters)
+        if code != 0:
+            raise RuntimeError(f'NavierStokes GMRES: Failed to converge in {kr.iters} iterations')
+        if 'LGMRES_suc' in self._iprint:
+            print(f'NavierStokes GMRES: Converged in {kr.iters} evaluations with 2-norm {kr.resnorm}')
+        return x3
+
+    def _spectral_norm(self, r3):
+        """2-norm of the 3 x N residual array as a MATRIX (largest singular value) -- what
+        ``np.linalg.norm((res_u, res_v, res_cont), ord=2)`` computes at NS:255 -- from its 3x3 Gram matrix."""
+        d = self._dev
+        G = np.empty((3, 3))
+        for i in range(3):
+            for j in range(i, 3):
+                G[i, j] = G[j, i] = d.dot(r3[i], r3[j])
+        return float(np.sqrt(max(np.linalg.eigvalsh(G)[-1], 0.0)))
+
+    # ---- reference API -----------------------------------------------------------------------------------------------------
+    def _get_residuals(self, u, v, p, T):
+        """Momentum and continuity residuals with their boundary rows  (NS:93-121)."""
+        d = self._dev
+        for k, a in enumerate((u, v, p, T)):
+            d.to_device(a, self._in[k])
+        self._residual_dev(self._in[0], self._in[1], self._in[2], self._in[3], self._out)
+        return tuple(d.to_host(self._out[k]) for k in range(3))
+
+    def _calc_jacobians(self, u, v):
+        """Jacobian diagonals Re G_x u, Re G_y u, Re G_x v, Re G_y v about (u, v)  (NS:123-136)."""
+        d = self._dev
+        d.to_device(u, self._in[0])
+        d.to_device(v, self._in[1])
+        self._jacobians_dev(self._in[0], self._in[1])
+
+    def _get_dresiduals(self, du, dv, dp, dT=None):
+        """3-field Jacobian-vector product with boundary rows  (NS:138-160)."""
+        d = self._dev
+        if not (self._have_sys and self._have_jac):
+            raise RuntimeError('NavierStokes: _get_residuals and _calc_jacobians must precede _get_dresiduals')
+        for k, a in enumerate((du, dv, dp)):
+            d.to_device(a, self._in[k])
+        dTd = d.to_device(dT, self._in[3]) if dT is not None else None
+        st = self._state()
+        L.check(self._lib.sem_ns_jvp(d.ctx, C.byref(st), self._in[0].data_ptr(), self._in[1].data_ptr(),
+                                     self._in[2].data_ptr(), dTd.data_ptr() if dTd is not None else None,
+                                     self._out[0].data_ptr(), self._out[1].data_ptr(), self._out[2].data_ptr(),
+                                     d.stream), "sem_ns_jvp")
+        return tuple(d.to_host(self._out[k]) for k in range(3))
+
+    def _get_update(self, dres_u, dres_v, dres_cont, du0=None, dv0=None, dp0=None):
+        """Velocity and pressure differentials for given residual differentials  (NS:162-236)."""
+        d = self._dev
+        for k, a in enumerate((dres_u, dres_v, dres_cont)):
+            d.to_device(a, self._out[k])
+        for k, a in enumerate((du0, dv0, dp0)):
+            if a is not None:
+                d.to_device(a, self._x[k])
+            else:
+                self._x[k].zero_()
+        self._solve_dev(self._out, self._x)
+        return tuple(d.to_host(self._x[k]) for k in range(3))
+
+    def _get_solution(self, T, u0=None, v0=None, p0=None):
+        """Newton iteration, device resident; updates u0, v0, p0 in place like NS:248-267 and returns them."""
+        d = self._dev
+        u = u0 if u0 is not None else np.zeros(self.N)
+        v = v0 if v0 is not None else np.zeros(self.N)
+        p = p0 if p0 is not None else np.zeros(self.N)
+        state = d.zeros(3)
+        for k, a in enumerate((u, v, p)):
+            d.to_device(a, state[k])
+        Td = d.to_device(T, self._in[3])
+        res, rhs = self._out, d.zeros(3)
+        self._k = 0
+        while True:
+            self._residual_dev(state[0], state[1], state[2], Td, res)
+            norm = self._spectral_norm(res)
+            if 'NEWTON_iter' in self._iprint:
+                print(f'NavierStokes NEWTON: {self._k}\t{norm}')
+            if norm <= self._mtol_newton * np.sqrt(self.N * 3):                      # NS:258
+                if 'NEWTON_suc' in self._iprint:
+                    r = np.array([d.to_host(res[k]) for k in range(3)])
+                    print(f'NavierStokes NEWTON: Converged in {self._k} iterations'
+                          f' with max-norm {np.linalg.norm(r, ord=np.inf)}')
+                break
+            if self._k >= self._max_newton:
+                raise RuntimeError(f'NavierStokes NEWTON: Failed to converge in {self._k} iterations')
+            self._jacobians_dev(state[0], state[1])
+            d.axpby(-1.0, res, 0.0, rhs)
+            self._x.zero_()
+            self._solve_dev(rhs, self._x)
+            d.axpby(1.0, self._x, 1.0, state)                                        # u += du; v += dv; p += dp
+            self._k += 1
+        for k, a in enumerate((u, v, p)):
+            np.copyto(a, d.to_host(state[k]))
+        return u, v, p
+
+    def _get_vector(self, f_func):
+        """f evaluated at the global nodes  (NS:272-278)."""
+        return f_func(self.points[0], self.points[1])
+
+    def _get_interpol(self, f, points_plot):
+        """Interpolation of the global vector f at plotting points  (NS:280-288)."""
+        d = self._dev
+        f_e = d.scatter(d.to_device(f, self._in[3])).cpu().numpy()
+        return SEM.eval_interpolation(f_e, self.points_e, points_plot)
+
+    def run(self, T_func, points_plot):
+        """Solution at plotting points  (NS:290-303)."""
+        T = self._get_vector(T_func)
+        u, v, p = self._get_solution(T)
+        return self._get_interpol(u, points_plot), self._get_interpol(v, points_plot), \
+            self._get_interpol(p, points_plot)

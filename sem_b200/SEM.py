@@ -1,0 +1,167 @@
+"""Continuous-Galerkin SEM on the uniform Cartesian element grid -- public functions of the reference's
+``Solvers/SEM.py`` on top of the GPU path.
+
+Mesh bookkeeping (nodes, index map) stays on the host.  Assembly (``assemble`` of 4-index arrays), ``scatter`` and the
+global operators run on the device: ``global_*_matrix`` return matrix-free operator objects whose ``@`` launches the
+fused sum-factorised kernel instead of materialising SciPy/``sparse`` matrices (the dense ``(P+1)^6``-per-element
+temporaries of SEM.py:243-244 are never formed).
+"""
+import typing
+
+import numpy as np
+import torch
+
+from . import GLL
+from .device import SemDevice
+
+
+def xi2x(e, xi, dx):
+    """Physical coordinate of standard coordinate xi in element e  (SEM.py:11-20)."""
+    if np.any(np.asarray(xi) > 1) or np.any(np.asarray(xi) < -1):
+        raise ValueError('xi out of range')
+    return dx / 2 * (xi + 1) + dx * e
+
+
+def x2xi(x, dx):
+    """(element, xi) of a physical coordinate; shared nodes go to the left element  (SEM.py:23-36)."""
+    frac, e = np.modf(np.asarray(x, dtype=np.float64) / dx)
+    xi = 2 * frac - 1
+    shift = np.isclose(xi, -1) * (e > 0)
+    e[shift] -= 1
+    xi[shift] = 1
+    return e.astype(int), xi
+
+
+def element_nodes_1d(P, N_ex, dx):
+    """x[m, k]  (SEM.py:39-48)."""
+    xi = GLL.standard_nodes(P)[0]
+    return np.vstack([xi2x(m, xi, dx) for m in range(N_ex)])
+
+
+def global_nodes_1d(P, N_ex, dx):
+    """Global 1-D nodes: element nodes without the duplicated first node  (SEM.py:51-60)."""
+    xe = element_nodes_1d(P, N_ex, dx)
+    return np.insert(np.ravel(xe[:, 1:]), 0, 0)
+
+
+def element_nodes(P, N_ex, N_ey, dx, dy):
+    """[x[m,n,k,l], y[m,n,k,l]]  (SEM.py:63-79), built by broadcasting instead of the (m, n) loop."""
+    xe = element_nodes_1d(P, N_ex, dx)
+    ye = element_nodes_1d(P, N_ey, dy)
+    pts = np.empty((2, N_ex, N_ey, P + 1, P + 1))
+    pts[0] = xe[:, None, :, None]
+    pts[1] = ye[None, :, None, :]
+    return pts
+
+
+def global_nodes(P, N_ex, N_ey, dx, dy):
+    """[x_p, y_p], x slow / y fast  (SEM.py:82-94)."""
+    x1 = global_nodes_1d(P, N_ex, dx)
+    y1 = global_nodes_1d(P, N_ey, dy)
+    return np.reshape(np.array(np.meshgrid(x1, y1, indexing='ij')), (2, x1.size * y1.size))
+
+
+def global_index(P, N_ex, N_ey, m, n, i, j):
+    """Local -> global index  (SEM.py:97-110)."""
+    if np.any(m >= N_ex) or np.any(n >= N_ey) or np.any(i > P) or np.any(j > P):
+        raise ValueError('Indices out of range')
+    return n * P + j + (N_ey * P + 1) * (m * P + i)
+
+
+def _device_for(P, N_ex, N_ey, dx=1.0, dy=1.0, _cache={}):
+    key = (P, N_ex, N_ey, float(dx), float(dy))
+    if key not in _cache:
+        _cache[key] = SemDevice(P, N_ex, N_ey, dx, dy)
+    return _cache[key]
+
+
+def assemble(A_e: np.ndarray):
+    """Gather-scatter of a 4-index element array A[m,n,i,j] into a global vector  (SEM.py:113-131).
+
+    Runs the colour-ordered, atomic-free device kernel (bitwise reproducible).  6- and 8-index arrays are what the
+    matrix-free path removes; use ``global_*_matrix`` (matrix-free operators) instead.
+    """
+    A_e = np.asarray(A_e, dtype=np.float64)
+    if A_e.ndim != 4:
+        raise NotImplementedError("sem_b200 assembles 4-index element arrays; element matrices are applied "
+                                  "matrix-free (see global_stiffness_matrix / global_gradient_matrices)")
+    N_ex, N_ey, P = A_e.shape[0], A_e.shape[1], A_e.shape[2] - 1
+    dev = _device_for(P, N_ex, N_ey)
+    elem = torch.from_numpy(np.ascontiguousarray(A_e)).to(dev.tdev)
+    return dev.to_host(dev.gather_scatter(elem))
+
+
+def scatter(u: np.ndarray, P: int, N_ex: int, N_ey: int):
+    """Global vector -> element array u[m,n,i,j]  (SEM.py:149-167) through the device scatter kernel."""
+    u = np.asarray(u, dtype=np.float64)
+    if u.shape[0] != (P * N_ex + 1) * (P * N_ey + 1):
+        raise ValueError('Not a valid combination of global coefficients vector, P, N_ex, and N_ey')
+    dev = _device_for(P, N_ex, N_ey)
+    return dev.scatter(dev.to_device(u)).cpu().numpy()
+
+
+class _MatrixFree:
+    """Stand-in for the CSR matrices of SEM.py:170-223: ``op @ x`` launches the fused device kernel."""
+
+    def __init__(self, dev, kind):
+        self._dev, self._kind = dev, kind
+        self.shape = (dev.NX * dev.NY,) * 2
+
+    def __matmul__(self, x):
+        dev = self._dev
+        xd = dev.to_device(x)
+        y = dev.zeros()
+        if self._kind == 'M':
+            dev.apply_mass(xd, y)
+        elif self._kind == 'K':
+            dev.apply_stiffness(xd, y)
+        elif self._kind == 'Gx':
+            dev.apply_gradient(xd, y, None)
+        else:
+            dev.apply_gradient(xd, None, y)
+        return dev.to_host(y)
+
+    def diagonal(self):
+        if self._kind != 'M':
+            raise NotImplementedError
+        return self._dev.to_host(self._dev.mass_diag())
+
+
+def global_mass_matrix(P, N_ex, N_ey, dx, dy):
+    """Matrix-free M  (SEM.py:170-183)."""
+    return _MatrixFree(_device_for(P, N_ex, N_ey, dx, dy), 'M')
+
+
+def global_stiffness_matrix(P, N_ex, N_ey, dx, dy):
+    """Matrix-free K  (SEM.py:186-203)."""
+    return _MatrixFree(_device_for(P, N_ex, N_ey, dx, dy), 'K')
+
+
+def global_gradient_matrices(P, N_ex, N_ey, dx, dy):
+    """Matrix-free G_x, G_y  (SEM.py:206-223)."""
+    dev = _device_for(P, N_ex, N_ey, dx, dy)
+    return _MatrixFree(dev, 'Gx'), _MatrixFree(dev, 'Gy')
+
+
+def global_convection_matrices(P, N_ex, N_ey, dx, dy):
+    """The N x N x N tensors of SEM.py:226-245 are never built: ``u @ C_x == diag(u) G_x`` and
+    ``C_x @ T == diag(G_x T)``; the solvers use those identities inside the fused kernels."""
+    raise NotImplementedError("convection tensors are applied matrix-free: u@C_x = diag(u) G_x, C_x@T = diag(G_x T)")
+
+
+def eval_interpolation(u_e: np.ndarray, points_e: np.ndarray, points_plot: typing.Tuple[np.ndarray, np.ndarray]):
+    """Evaluate the SEM interpolant of u_e[m,n,k,l] on an ij-meshgrid  (SEM.py:248-273).
+
+    Host-side tensor-product evaluation, one gathered einsum instead of the (m, n) double loop.
+    """
+    P = u_e.shape[2] - 1
+    x_e = points_e[0, :, 0, :, 0]
+    y_e = points_e[1, 0, :, 0, :]
+    dx = x_e[0, -1] - x_e[0, 0]
+    dy = y_e[0, -1] - y_e[0, 0]
+    m_p, xi_p = x2xi(points_plot[0][:, 0], dx)
+    n_p, eta_p = x2xi(points_plot[1][0, :], dy)
+    Sx = GLL.standard_evaluation_matrix(P, xi_p)      # [a, k]
+    Sy = GLL.standard_evaluation_matrix(P, eta_p)     # [b, l]
+    tmp = np.einsum('ankl,ak->anl', u_e[m_p], Sx)     # contract x inside each plot column's element column
+    return np.einsum('abl,bl->ab', tmp[:, n_p, :], Sy)

@@ -1,0 +1,486 @@
+// C ABI of sem_b200 (see include/sem_b200.h): context, host<->device packing, fused operators, Krylov solvers.
+#include "../../include/sem_b200.h"
+#include "sem_aux.cuh"
+#include "sem_dispatch.h"
+#include "sem_march.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+namespace semb {
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+}  // namespace semb
+
+using namespace semb;
+
+typedef int (*march_fn)(int, const MeshDev&, const MarchArgs&, const MarchGeom&, cudaStream_t);
+typedef size_t (*smem_fn)(int, int);
+typedef int (*upload_fn)(const double*, const double*, const double*);
+
+#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P},
+static const struct {
+    march_fn launch;
+    smem_fn smem;
+    upload_fn upload;
+} g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
+
+struct sem_ctx {
+    MeshDev g;
+    int device, sm_count, smem_optin;
+    int Ty_req, Mx_req;
+    int pin_gx, pin_iy;
+    double *dD, *dKs, *dw;   // plain device tables
+    double* dKdiag;          // diag(K), built on first use
+    RedScratch rs;
+    double* d_small;         // device staging for reduction results
+    double* h_small;         // pinned mirror
+    int small_len;
+    TabDev tab() const { return TabDev{dD, dKs, dw}; }
+};
+
+#define SEM_CHECK_CTX(ctx)                              \
+    do {                                                \
+        if (!(ctx)) {                                   \
+            set_error("null context");                  \
+            return -2;                                  \
+        }                                               \
+        SEM_CUDA(cudaSetDevice((ctx)->device));         \
+    } while (0)
+
+static const int SEM_MAX_RESTART = 4096;
+
+extern "C" const char* sem_last_error(void) { return g_err.c_str(); }
+extern "C" int sem_version(void) { return 100; }
+
+extern "C" int sem_ctx_create(sem_ctx** out, const sem_mesh_desc* d) {
+    if (!out || !d) { set_error("sem_ctx_create: null argument"); return -2; }
+    if (d->P < 1 || d->P > SEM_MAX_P) { set_error("sem_ctx_create: P must be in 1..16"); return -2; }
+    if (d->N_ex < 1 || d->N_ey < 1 || d->m_begin < 0 || d->m_end > d->N_ex || d->m_begin >= d->m_end) {
+        set_error("sem_ctx_create: bad element counts / partition");
+        return -2;
+    }
+    SEM_CUDA(cudaSetDevice(d->device));
+    sem_ctx* c = new sem_ctx();
+    std::memset(c, 0, sizeof(*c));
+    c->device = d->device;
+    SEM_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, d->device));
+    SEM_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+    MeshDev& g = c->g;
+    g.P = d->P;
+    g.nex = d->m_end - d->m_begin;
+    g.ney = d->N_ey;
+    g.NX = g.nex * g.P + 1;
+    g.NY = g.ney * g.P + 1;
+    g.LD = round_up(g.NY, 16);
+    g.gx0 = d->m_begin * g.P;
+    g.NXg = d->N_ex * g.P + 1;
+    g.has_left = d->m_begin > 0;
+    g.has_right = d->m_end < d->N_ex;
+    g.dx = d->dx;
+    g.dy = d->dy;
+    if ((long long)g.NX * g.LD >= (1ll << 31)) { set_error("sem_ctx_create: slab too large for 32-bit offsets"); delete c; return -2; }
+    const long long Nglob = (long long)g.NXg * g.NY;
+    const long long pin = Nglob / 2;   // int(N/2), NS:89
+    c->pin_gx = (int)(pin / g.NY);
+    c->pin_iy = (int)(pin % g.NY);
+    const int n = g.P + 1;
+    SEM_CUDA(cudaMalloc(&c->dD, sizeof(double) * n * n));
+    SEM_CUDA(cudaMalloc(&c->dKs, sizeof(double) * n * n));
+    SEM_CUDA(cudaMalloc(&c->dw, sizeof(double) * n));
+    SEM_CUDA(cudaMemcpy(c->dD, d->D, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    SEM_CUDA(cudaMemcpy(c->dKs, d->Ks, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    SEM_CUDA(cudaMemcpy(c->dw, d->w, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (g_orders[g.P - 1].upload(d->D, d->Ks, d->w)) { delete c; return -1; }
+    c->rs.max_blocks = 2 * c->sm_count;
+    c->rs.max_k = SEM_MAX_RESTART + 8;
+    SEM_CUDA(cudaMalloc(&c->rs.partials, sizeof(double) * (size_t)c->rs.max_blocks * c->rs.max_k));
+    SEM_CUDA(cudaMalloc(&c->rs.counter, sizeof(unsigned) * (c->rs.max_k / 8 + 1)));
+    SEM_CUDA(cudaMemset(c->rs.counter, 0, sizeof(unsigned) * (c->rs.max_k / 8 + 1)));
+    c->small_len = 2 * SEM_MAX_RESTART + 64;
+    SEM_CUDA(cudaMalloc(&c->d_small, sizeof(double) * c->small_len));
+    SEM_CUDA(cudaMallocHost(&c->h_small, sizeof(double) * c->small_len));
+    *out = c;
+    return 0;
+}
+
+extern "C" void sem_ctx_destroy(sem_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->dD); cudaFree(c->dKs); cudaFree(c->dw);
+    if (c->dKdiag) cudaFree(c->dKdiag);
+    cudaFree(c->rs.partials); cudaFree(c->rs.counter);
+    cudaFree(c->d_small); cudaFreeHost(c->h_small);
+    delete c;
+}
+
+extern "C" int sem_ctx_ld(const sem_ctx* c) { return c ? c->g.LD : -1; }
+extern "C" int sem_ctx_nx(const sem_ctx* c) { return c ? c->g.NX : -1; }
+extern "C" int sem_ctx_ny(const sem_ctx* c) { return c ? c->g.NY : -1; }
+extern "C" long long sem_ctx_vec_len(const sem_ctx* c) { return c ? (long long)c->g.NX * c->g.LD : -1; }
+extern "C" int sem_ctx_set_tiling(sem_ctx* c, int Ty, int Mx) {
+    if (!c) return -2;
+    c->Ty_req = Ty;
+    c->Mx_req = Mx;
+    return 0;
+}
+
+extern "C" int sem_h2d(sem_ctx* c, const double* host, double* vec, void* stream) {
+    SEM_CHECK_CTX(c);
+    const MeshDev& g = c->g;
+    SEM_CUDA(cudaMemcpy2DAsync(vec, sizeof(double) * g.LD, host, sizeof(double) * g.NY, sizeof(double) * g.NY, g.NX,
+                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int sem_d2h(sem_ctx* c, const double* vec, double* host, void* stream) {
+    SEM_CHECK_CTX(c);
+    const MeshDev& g = c->g;
+    SEM_CUDA(cudaMemcpy2DAsync(host, sizeof(double) * g.NY, vec, sizeof(double) * g.LD, sizeof(double) * g.NY, g.NX,
+                               cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SEM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
+    A.zero = 0;
+    MarchGeom q = march_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
+    // shrink the strip until the tile fits the opt-in shared memory of the device
+    while (g_orders[c->g.P - 1].smem(mode, q.pitch) > (size_t)c->smem_optin && q.Ty > 1) {
+        q = march_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count);
+    }
+    return g_orders[c->g.P - 1].launch(mode, c->g, A, q, st);
+}
+
+static MarchArgs zero_args() {
+    MarchArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.bc.pin_gx = -1;
+    A.bc.pin_iy = -1;
+    return A;
+}
+
+static void fill_cd_bc(BCSpec& bc, const sem_cd_bc& in, int residual) {
+    for (int s = 0; s < 4; ++s) {
+        bc.active[s] = in.active[s];
+        bc.val0[s] = in.value[s];
+        bc.val1[s] = 0.0;
+    }
+    bc.residual = residual;
+    bc.pin_gx = bc.pin_iy = -1;
+}
+
+static void fill_ns_bc(const sem_ctx* c, BCSpec& bc, const sem_ns_bc& in, int residual) {
+    // NS:78-88: W, E, S, N in that order, later wins: (u,v) = (0,v_W), (0,v_E), (u_S,0), (u_N,0)
+    const double u[4] = {0.0, 0.0, in.u_S, in.u_N};
+    const double v[4] = {in.v_W, in.v_E, 0.0, 0.0};
+    for (int s = 0; s < 4; ++s) {
+        bc.active[s] = 1;
+        bc.val0[s] = u[s];
+        bc.val1[s] = v[s];
+    }
+    bc.residual = residual;
+    bc.pin_gx = c->pin_gx;
+    bc.pin_iy = c->pin_iy;
+}
+
+extern "C" int sem_apply_stiffness(sem_ctx* c, const double* x, double* y, void* stream) {
+    SEM_CHECK_CTX(c);
+    MarchArgs A = zero_args();
+    A.a = x;
+    A.y0 = y;
+    return march(c, MODE_K, A, (cudaStream_t)stream);
+}
+
+extern "C" int sem_apply_gradient(sem_ctx* c, const double* x, double scale, double* gx, double* gy, void* stream) {
+    SEM_CHECK_CTX(c);
+    MarchArgs A = zero_args();
+    A.a = x;
+    A.y0 = gx;
+    A.y1 = gy;
+    A.cconv = scale;
+    return march(c, MODE_G, A, (cudaStream_t)stream);
+}
+
+extern "C" int sem_apply_mass(sem_ctx* c, const double* x, double* y, void* stream) {
+    SEM_CHECK_CTX(c);
+    return aux_mass_apply(c->g, c->tab(), x, y, (cudaStream_t)stream);
+}
+
+extern "C" int sem_mass_diag(sem_ctx* c, double* m, void* stream) {
+    SEM_CHECK_CTX(c);
+    return aux_mass_apply(c->g, c->tab(), nullptr, m, (cudaStream_t)stream);
+}
+
+extern "C" int sem_gather_scatter(sem_ctx* c, const double* elem, double* y, void* stream) {
+    SEM_CHECK_CTX(c);
+    return aux_gather_scatter(c->g, elem, y, (cudaStream_t)stream);
+}
+
+extern "C" int sem_scatter(sem_ctx* c, const double* x, double* elem, void* stream) {
+    SEM_CHECK_CTX(c);
+    return aux_scatter(c->g, x, elem, (cudaStream_t)stream);
+}
+
+// ---- convection-diffusion ---------------------------------------------------------------------------------------
+extern "C" int sem_cd_residual(sem_ctx* c, const sem_cd_state* s, const double* T, double* res, void* stream) {
+    SEM_CHECK_CTX(c);
+    MarchArgs A = zero_args();
+    A.a = T; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = res;
+    fill_cd_bc(A.bc, s->bc, 1);
+    return march(c, MODE_CD, A, (cudaStream_t)stream);
+}
+
+extern "C" int sem_cd_jacobians(sem_ctx* c, double Pe, const double* T, double* gxT, double* gyT, void* stream) {
+    return sem_apply_gradient(c, T, Pe, gxT, gyT, stream);
+}
+
+extern "C" int sem_cd_jvp(sem_ctx* c, const sem_cd_state* s, const double* dT, const double* du, const double* dv,
+                          double* dres, void* stream) {
+    SEM_CHECK_CTX(c);
+    if ((du || dv) && (!s->gxT || !s->gyT)) { set_error("sem_cd_jvp: du/dv given but no Jacobians in the state"); return -2; }
+    MarchArgs A = zero_args();
+    A.a = dT; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = dres;
+    A.d0 = s->gxT; A.e0 = du; A.d1 = s->gyT; A.e1 = dv;
+    fill_cd_bc(A.bc, s->bc, 0);
+    return march(c, MODE_CD, A, (cudaStream_t)stream);
+}
+
+// ---- Navier-Stokes ------------------------------------------------------------------------------------------------
+extern "C" int sem_ns_residual(sem_ctx* c, const sem_ns_state* s, const double* u, const double* v, const double* p,
+                               const double* T, double* ru, double* rv, double* rc, void* stream) {
+    SEM_CHECK_CTX(c);
+    MarchArgs A = zero_args();
+    A.a = u; A.b = v; A.c = p; A.U = u; A.V = v; A.cconv = s->Re;
+    A.e0 = T; A.cbuoy = -s->Gr_over_Re;
+    A.y0 = ru; A.y1 = rv; A.y2 = rc;
+    fill_ns_bc(c, A.bc, s->bc, 1);
+    int rcode = march(c, MODE_NS, A, (cudaStream_t)stream);
+    if (rcode) return rcode;
+    // NS:116-119: pin first, then the Neumann rows (they win if the pin sits on the boundary)
+    return aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, (cudaStream_t)stream);
+}
+
+extern "C" int sem_ns_jacobians(sem_ctx* c, double Re, const double* u, const double* v, double* gxu, double* gyu,
+                                double* gxv, double* gyv, void* stream) {
+    int r = sem_apply_gradient(c, u, Re, gxu, gyu, stream);
+    if (r) return r;
+    return sem_apply_gradient(c, v, Re, gxv, gyv, stream);
+}
+
+extern "C" int sem_ns_jvp(sem_ctx* c, const sem_ns_state* s, const double* du, const double* dv, const double* dp,
+                          const double* dT, double* ou, double* ov, double* oc, void* stream) {
+    SEM_CHECK_CTX(c);
+    if (!s->gxu || !s->gyu || !s->gxv || !s->gyv) { set_error("sem_ns_jvp: Jacobians missing in the state"); return -2; }
+    MarchArgs A = zero_args();
+    A.a = du; A.b = dv; A.c = dp; A.U = s->u; A.V = s->v; A.cconv = s->Re;
+    A.d0 = s->gxu; A.d1 = s->gyu; A.d2 = s->gxv; A.d3 = s->gyv;
+    A.e0 = dT; A.cbuoy = -s->Gr_over_Re;
+    A.y0 = ou; A.y1 = ov; A.y2 = oc;
+    fill_ns_bc(c, A.bc, s->bc, 0);
+    int rcode = march(c, MODE_NS, A, (cudaStream_t)stream);
+    if (rcode) return rcode;
+    // NS:157-158: Neumann rows first, then the pin (the pin wins)
+    return aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, (cudaStream_t)stream);
+}
+
+// ---- reductions ------------------------------------------------------------------------------------------------------
+extern "C" int sem_dot(sem_ctx* c, const double* x, const double* y, long long n, double* host_out, void* stream) {
+    SEM_CHECK_CTX(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aux_multi_dot(x, n, 1, y, c->d_small, 1, n, 0, c->rs, st)) return -1;
+    SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SEM_CUDA(cudaStreamSynchronize(st));
+    *host_out = c->h_small[0];
+    return 0;
+}
+
+extern "C" int sem_axpby(sem_ctx* c, double a, const double* x, double b, double* y, long long n, void* stream) {
+    SEM_CHECK_CTX(c);
+    return aux_axpby(a, x, b, y, n, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Right-preconditioned restarted GMRES with CGS2 orthogonalisation (two classical Gram-Schmidt passes, each one
+// batched dot kernel + one batched update kernel).  Replaces scipy.sparse.linalg.lgmres of CD:146-148 / NS:222-224.
+// The stopping rule is the reference's: true residual 2-norm <= atol (right preconditioning keeps the Arnoldi
+// residual equal to the true residual; it is re-evaluated explicitly before returning).
+// ---------------------------------------------------------------------------------------------------------------
+typedef std::function<int(const double*, double*)> vecop;
+
+struct GmresLayout {
+    long long n;     // doubles per multi-vector
+    int nf;          // fields per multi-vector
+    long long vlen;  // doubles per field
+};
+
+static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop& Pinv, const double* b, double* x,
+                 sem_krylov* kr, double* V, double* w, double* t, cudaStream_t st) {
+    const long long n = L.n;
+    int m = kr->restart;
+    if (m < 1) m = 1;
+    if (m > SEM_MAX_RESTART) m = SEM_MAX_RESTART;
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gv(m + 1), yv(m);
+    kr->iters = 0;
+    kr->resnorm = -1.0;
+    const long long skip = 0;
+    auto norm2 = [&](const double* v, double* out) -> int {
+        if (aux_multi_dot(v, n, 1, v, c->d_small, L.nf, L.vlen, skip, c->rs, st)) return -1;
+        SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SEM_CUDA(cudaStreamSynchronize(st));
+        *out = std::sqrt(c->h_small[0]);
+        return 0;
+    };
+    // r0 = b - A x  -> V0
+    if (Aop(x, w)) return -1;
+    if (aux_axpby(1.0, b, 0.0, V, n, st)) return -1;
+    if (aux_axpby(-1.0, w, 1.0, V, n, st)) return -1;
+    double beta;
+    if (norm2(V, &beta)) return -1;
+    if (kr->verbose) fprintf(stderr, "[sem gmres] start |r| = %.6e  atol = %.3e  n = %lld restart = %d\n", beta, kr->atol, n, m);
+    while (true) {
+        kr->resnorm = beta;
+        if (!(beta > kr->atol)) return 0;
+        if (kr->iters >= kr->max_iters) return kr->iters > 0 ? kr->iters : 1;
+        if (aux_axpby(1.0 / beta, V, 0.0, w, n, st)) return -1;
+        if (aux_axpby(1.0, w, 0.0, V, n, st)) return -1;
+        gv.assign(m + 1, 0.0);
+        gv[0] = beta;
+        int j = 0;
+        double est = beta;
+        for (; j < m; ++j) {
+            const double* Vj = V + (long long)j * n;
+            if (Pinv(Vj, t)) return -1;
+            if (Aop(t, w)) return -1;
+            kr->iters++;
+            double* h1 = c->d_small;
+            double* h2 = c->d_small + (j + 1);
+            double* nr = c->d_small + 2 * (j + 1);
+            if (aux_multi_dot(V, n, j + 1, w, h1, L.nf, L.vlen, skip, c->rs, st)) return -1;
+            if (aux_multi_axpy(V, n, j + 1, h1, -1.0, w, st)) return -1;
+            if (aux_multi_dot(V, n, j + 1, w, h2, L.nf, L.vlen, skip, c->rs, st)) return -1;
+            if (aux_multi_axpy(V, n, j + 1, h2, -1.0, w, st)) return -1;
+            if (aux_multi_dot(w, n, 1, w, nr, L.nf, L.vlen, skip, c->rs, st)) return -1;
+            if (aux_scale_inv_norm(w, nr, V + (long long)(j + 1) * n, n, st)) return -1;
+            SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double) * (2 * (j + 1) + 1), cudaMemcpyDeviceToHost, st));
+            SEM_CUDA(cudaStreamSynchronize(st));
+            double* Hj = &H[(size_t)j * (m + 1)];   // column j
+            for (int i = 0; i <= j; ++i) Hj[i] = c->h_small[i] + c->h_small[j + 1 + i];
+            const double hn = std::sqrt(c->h_small[2 * (j + 1)]);
+            Hj[j + 1] = hn;
+            for (int i = 0; i < j; ++i) {
+                const double a = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
+                Hj[i + 1] = -sn[i] * Hj[i] + cs[i] * Hj[i + 1];
+                Hj[i] = a;
+            }
+            const double d = std::hypot(Hj[j], Hj[j + 1]);
+            cs[j] = d > 0 ? Hj[j] / d : 1.0;
+            sn[j] = d > 0 ? Hj[j + 1] / d : 0.0;
+            Hj[j] = d;
+            Hj[j + 1] = 0.0;
+            gv[j + 1] = -sn[j] * gv[j];
+            gv[j] = cs[j] * gv[j];
+            est = std::fabs(gv[j + 1]);
+            if (kr->verbose > 1 || (kr->verbose && kr->iters % 100 == 0))
+                fprintf(stderr, "[sem gmres] it %d  |r| ~ %.6e\n", kr->iters, est);
+            if (!std::isfinite(est)) { set_error("gmres: non-finite residual"); return -3; }
+            if (est <= kr->atol || kr->iters >= kr->max_iters || !(hn > 0.0)) { ++j; break; }
+        }
+        // y = H^-1 g (back substitution on the rotated upper-triangular H), x += Pinv(V y)
+        const int k = j;
+        for (int i = k - 1; i >= 0; --i) {
+            double s = gv[i];
+            for (int q = i + 1; q < k; ++q) s -= H[(size_t)q * (m + 1) + i] * yv[q];
+            yv[i] = s / H[(size_t)i * (m + 1) + i];
+        }
+        std::memcpy(c->h_small, yv.data(), sizeof(double) * k);
+        SEM_CUDA(cudaMemcpyAsync(c->d_small, c->h_small, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+        if (aux_multi_comb(V, n, k, c->d_small, w, st)) return -1;
+        if (Pinv(w, t)) return -1;
+        if (aux_axpby(1.0, t, 1.0, x, n, st)) return -1;
+        // true residual
+        if (Aop(x, w)) return -1;
+        if (aux_axpby(1.0, b, 0.0, V, n, st)) return -1;
+        if (aux_axpby(-1.0, w, 1.0, V, n, st)) return -1;
+        if (norm2(V, &beta)) return -1;
+        if (kr->verbose) fprintf(stderr, "[sem gmres] cycle end: its %d  true |r| = %.6e (estimate %.3e)\n", kr->iters, beta, est);
+    }
+}
+
+static int ensure_kdiag(sem_ctx* c, cudaStream_t st) {
+    if (c->dKdiag) return 0;
+    SEM_CUDA(cudaMalloc(&c->dKdiag, sizeof(double) * (size_t)c->g.NX * c->g.LD));
+    return aux_stiffness_diag(c->g, c->tab(), c->dKdiag, st);
+}
+
+extern "C" long long sem_cd_work_len(const sem_ctx* c, int restart) {
+    if (!c) return -1;
+    return (long long)(restart + 1 + 2) * c->g.NX * c->g.LD;
+}
+
+extern "C" int sem_cd_solve(sem_ctx* c, const sem_cd_state* s, const double* rhs, double* dT, sem_krylov* kr,
+                            double* work, long long work_len, void* stream) {
+    SEM_CHECK_CTX(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    if (kr->restart > SEM_MAX_RESTART) kr->restart = SEM_MAX_RESTART;
+    if (work_len < sem_cd_work_len(c, kr->restart)) { set_error("sem_cd_solve: work buffer too small"); return -2; }
+    if (ensure_kdiag(c, st)) return -1;
+    double* V = work;
+    double* w = work + (long long)(kr->restart + 1) * vlen;
+    double* t = w + vlen;
+    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * 2 * vlen, st));
+    sem_cd_state lin = *s;
+    BCSpec bc;
+    fill_cd_bc(bc, s->bc, 0);
+    vecop Aop = [&](const double* xx, double* yy) { return sem_cd_jvp(c, &lin, xx, nullptr, nullptr, yy, stream); };
+    vecop Pinv = [&](const double* r, double* z) {
+        if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, vlen, st);
+        return aux_cd_jacobi(c->g, bc, c->dKdiag, r, z, st);
+    };
+    GmresLayout L{vlen, 1, vlen};
+    return gmres(c, L, Aop, Pinv, rhs, dT, kr, V, w, t, st);
+}
+
+extern "C" long long sem_ns_work_len(const sem_ctx* c, int restart) {
+    if (!c) return -1;
+    return ((long long)(restart + 1 + 2) * 3 + 1) * c->g.NX * c->g.LD;
+}
+
+extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs3, double* x3, sem_krylov* kr,
+                            double* work, long long work_len, void* stream) {
+    SEM_CHECK_CTX(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    const long long n = 3 * vlen;
+    if (kr->restart > SEM_MAX_RESTART) kr->restart = SEM_MAX_RESTART;
+    if (work_len < sem_ns_work_len(c, kr->restart)) { set_error("sem_ns_solve: work buffer too small"); return -2; }
+    if (ensure_kdiag(c, st)) return -1;
+    double* V = work;
+    double* w = work + (long long)(kr->restart + 1) * n;
+    double* t = w + n;
+    double* tmp = t + n;
+    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (2 * n + vlen), st));
+    sem_ns_state lin = *s;
+    vecop Aop = [&](const double* xx, double* yy) {
+        return sem_ns_jvp(c, &lin, xx, xx + vlen, xx + 2 * vlen, nullptr, yy, yy + vlen, yy + 2 * vlen, stream);
+    };
+    // Block lower-triangular right preconditioner  [[P_a, 0], [C, M_p]]^-1  with P_a = Jacobi on the velocity block,
+    // C = continuity rows, M_p = diagonal mass with the pin row passed through (the reference's Schur preconditioner,
+    // NS:208-212).  With this structure GMRES converges to the same member of the (singular, consistent) system's
+    // solution family as the reference's Schur-complement iteration -- see DESIGN.md.
+    vecop Pinv = [&](const double* r, double* z) {
+        if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, n, st);
+        if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) return -1;
+        MarchArgs A = zero_args();
+        A.a = z; A.b = z + vlen; A.y0 = tmp;
+        if (march(c, MODE_DIV, A, st)) return -1;
+        return aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st);
+    };
+    GmresLayout L{n, 3, vlen};
+    return gmres(c, L, Aop, Pinv, rhs3, x3, kr, V, w, t, st);
+}

@@ -26,11 +26,13 @@ struct MeshDev {
 
 // 1-D GLL tables of order P in constant memory: every DFMA of the sum-factorised contractions takes its table
 // operand straight from the constant bank (uniform across the warp), leaving shared memory to the nodal data.
+// Rows are padded to an even length so that every row starts 16-byte aligned (LDCU.128 fetches two operands).
 template <int P>
-struct Tab {
-    double D[(P + 1) * (P + 1)];   // D[i][k] = l_k'(xi_i)                      GLL.py:45-59
-    double Ks[(P + 1) * (P + 1)];  // Ks[i][k] = sum_q w_q D[q][i] D[q][k]       GLL.py:73-81
-    double w[P + 1];               // quadrature weights                         GLL.py:30
+struct __align__(16) Tab {
+    static constexpr int NP = (P + 2) / 2 * 2;   // padded row stride
+    double D[(P + 1) * NP];    // D[i][k] = l_k'(xi_i)                      GLL.py:45-59
+    double Ks[(P + 1) * NP];   // Ks[i][k] = sum_q w_q D[q][i] D[q][k]       GLL.py:73-81
+    double w[NP];              // quadrature weights                         GLL.py:30
 };
 template <int P>
 __constant__ Tab<P> c_tab;
@@ -59,7 +61,8 @@ enum MarchMode {
     MODE_K = 0,    // y0 = K a
     MODE_G = 1,    // y0 = s G_x a ; y1 = s G_y a                      (s = cconv)
     MODE_CD = 2,   // y0 = K a + cconv (U o G_x a + V o G_y a) [+ d0 o e0 + d1 o e1], Dirichlet rows
-    MODE_NS = 3    // 3-field Navier-Stokes residual / JVP
+    MODE_NS = 3,   // 3-field Navier-Stokes residual / JVP
+    MODE_DIV = 4   // y0 = G_x a + G_y b                               (continuity rows, used by the preconditioner)
 };
 
 struct MarchArgs {
@@ -79,6 +82,7 @@ struct MarchArgs {
     double* y2;
     double cconv;      // Re or Pe (or the scale of MODE_G)
     double cbuoy;      // coefficient of M o e0 in y1 (NS: -Gr/Re), 0 = off
+    int zero;          // always 0 (see opaque_zero in sem_march.cuh)
     BCSpec bc;
 };
 

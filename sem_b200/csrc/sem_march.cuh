@@ -29,13 +29,20 @@
 #pragma once
 #include "sem_common.cuh"
 
+#ifndef SEM_MARCH_MAXT
+#define SEM_MARCH_MAXT 320   // upper bound of the CTA size chosen by march_geometry()
+#endif
+
 namespace semb {
 
 template <int MODE> struct ModeTraits;
-template <> struct ModeTraits<MODE_K>  { static constexpr int NF = 1, NV = 0, NACC = 1, NOUT = 1; };
-template <> struct ModeTraits<MODE_G>  { static constexpr int NF = 1, NV = 0, NACC = 1, NOUT = 2; };
-template <> struct ModeTraits<MODE_CD> { static constexpr int NF = 1, NV = 1, NACC = 1, NOUT = 1; };
-template <> struct ModeTraits<MODE_NS> { static constexpr int NF = 3, NV = 1, NACC = 3, NOUT = 3; };
+// NF contracted fields, NV staged advecting component, NACC y-accumulators, NOUT outputs, MINB resident CTAs/SM
+// the register allocation is held to (ptxas -v: no spills at these bounds for P <= 8).
+template <> struct ModeTraits<MODE_K>  { static constexpr int NF = 1, NV = 0, NACC = 1, NOUT = 1, MINB = 3; };
+template <> struct ModeTraits<MODE_G>  { static constexpr int NF = 1, NV = 0, NACC = 1, NOUT = 2, MINB = 2; };
+template <> struct ModeTraits<MODE_CD> { static constexpr int NF = 1, NV = 1, NACC = 1, NOUT = 1, MINB = 2; };
+template <> struct ModeTraits<MODE_NS> { static constexpr int NF = 3, NV = 1, NACC = 3, NOUT = 3, MINB = 1; };
+template <> struct ModeTraits<MODE_DIV> { static constexpr int NF = 2, NV = 0, NACC = 1, NOUT = 1, MINB = 2; };
 
 // shared memory doubles per CTA
 template <int P, int MODE>
@@ -44,11 +51,25 @@ __host__ __device__ constexpr size_t march_smem_doubles(int pitch) {
 }
 
 // 1-D contraction of an element line with row I of a table (compile-time offsets into constant memory)
+// Opaque zero.  ptxas otherwise hoists all (P+1)^2 table loads out of the marching loop into registers (LICM), which
+// costs ~100 registers at P=8; an offset it cannot prove loop-invariant keeps them as just-in-time LDCU operands.
+__device__ __forceinline__ int opaque_zero(int zero_param) {
+    int z;
+    asm volatile("mov.u32 %0, %1;" : "=r"(z) : "r"(zero_param));
+    return z;
+}
+
 template <int P, int I>
 __device__ __forceinline__ double row_dot(const double* __restrict__ tab, const double (&r)[P + 1]) {
-    double s = tab[I * (P + 1)] * r[0];
+    constexpr int NP = Tab<P>::NP;
+    const double2* __restrict__ t2 = reinterpret_cast<const double2*>(tab + I * NP);   // 16-byte aligned row
+    double s = 0.0;
 #pragma unroll
-    for (int k = 1; k <= P; ++k) s = fma(tab[I * (P + 1) + k], r[k], s);
+    for (int kk = 0; kk < NP / 2; ++kk) {
+        const double2 c = t2[kk];
+        s = (kk == 0) ? c.x * r[0] : fma(c.x, r[2 * kk], s);
+        if (2 * kk + 1 <= P) s = fma(c.y, r[2 * kk + 1], s);
+    }
     return s;
 }
 
@@ -72,22 +93,26 @@ struct March {
     // ---- x-contraction of row I: contributions of ONE element to the NOUT outputs at its node (I, iy) ----------
     template <int I>
     static __device__ __forceinline__ void xrow(const double (&r)[NF][n], double Uc, double cKx, double wyA,
-                                                double cc, double (&x)[NOUT]) {
+                                                double cc, double (&x)[NOUT], int z) {
+        const double* tD = c_tab<P>.D + 2 * z;
+        const double* tK = c_tab<P>.Ks + 2 * z;
         const double gw = c_tab<P>.w[I] * wyA;
         if constexpr (MODE == MODE_K) {
-            x[0] = cKx * row_dot<P, I>(c_tab<P>.Ks, r[0]);
+            x[0] = cKx * row_dot<P, I>(tK, r[0]);
         } else if constexpr (MODE == MODE_G) {
-            x[0] = cc * gw * row_dot<P, I>(c_tab<P>.D, r[0]);
+            x[0] = cc * gw * row_dot<P, I>(tD, r[0]);
             x[1] = 0.0;
         } else if constexpr (MODE == MODE_CD) {
-            x[0] = fma(cc * Uc * gw, row_dot<P, I>(c_tab<P>.D, r[0]), cKx * row_dot<P, I>(c_tab<P>.Ks, r[0]));
+            x[0] = fma(cc * Uc * gw, row_dot<P, I>(tD, r[0]), cKx * row_dot<P, I>(tK, r[0]));
+        } else if constexpr (MODE == MODE_DIV) {
+            x[0] = gw * row_dot<P, I>(tD, r[0]);
         } else {
-            const double sDa = row_dot<P, I>(c_tab<P>.D, r[0]);
-            const double sDb = row_dot<P, I>(c_tab<P>.D, r[1]);
-            const double sDc = row_dot<P, I>(c_tab<P>.D, r[2]);
+            const double sDa = row_dot<P, I>(tD, r[0]);
+            const double sDb = row_dot<P, I>(tD, r[1]);
+            const double sDc = row_dot<P, I>(tD, r[2]);
             const double cu = cc * Uc * gw;
-            x[0] = fma(gw, sDc, fma(cu, sDa, cKx * row_dot<P, I>(c_tab<P>.Ks, r[0])));
-            x[1] = fma(cu, sDb, cKx * row_dot<P, I>(c_tab<P>.Ks, r[1]));
+            x[0] = fma(gw, sDc, fma(cu, sDa, cKx * row_dot<P, I>(tK, r[0])));
+            x[1] = fma(cu, sDb, cKx * row_dot<P, I>(tK, r[1]));
             x[2] = gw * sDa;
         }
     }
@@ -96,21 +121,25 @@ struct March {
     //      shared-memory accumulators at node (line, J) -------------------------------------------------------------
     template <int J>
     static __device__ __forceinline__ void yrow(const double (&l)[NF][n], double Vc, double wxK, double wxA,
-                                                double cc, double (&y)[NACC]) {
+                                                double cc, double (&y)[NACC], int z) {
+        const double* tD = c_tab<P>.D + 2 * z;
+        const double* tK = c_tab<P>.Ks + 2 * z;
         const double gw = wxA * c_tab<P>.w[J];
         if constexpr (MODE == MODE_K) {
-            y[0] = wxK * row_dot<P, J>(c_tab<P>.Ks, l[0]);
+            y[0] = wxK * row_dot<P, J>(tK, l[0]);
         } else if constexpr (MODE == MODE_G) {
-            y[0] = cc * gw * row_dot<P, J>(c_tab<P>.D, l[0]);
+            y[0] = cc * gw * row_dot<P, J>(tD, l[0]);
         } else if constexpr (MODE == MODE_CD) {
-            y[0] = fma(cc * Vc * gw, row_dot<P, J>(c_tab<P>.D, l[0]), wxK * row_dot<P, J>(c_tab<P>.Ks, l[0]));
+            y[0] = fma(cc * Vc * gw, row_dot<P, J>(tD, l[0]), wxK * row_dot<P, J>(tK, l[0]));
+        } else if constexpr (MODE == MODE_DIV) {
+            y[0] = gw * row_dot<P, J>(tD, l[1]);
         } else {
-            const double sDa = row_dot<P, J>(c_tab<P>.D, l[0]);
-            const double sDb = row_dot<P, J>(c_tab<P>.D, l[1]);
-            const double sDc = row_dot<P, J>(c_tab<P>.D, l[2]);
+            const double sDa = row_dot<P, J>(tD, l[0]);
+            const double sDb = row_dot<P, J>(tD, l[1]);
+            const double sDc = row_dot<P, J>(tD, l[2]);
             const double cv = cc * Vc * gw;
-            y[0] = fma(cv, sDa, wxK * row_dot<P, J>(c_tab<P>.Ks, l[0]));
-            y[1] = fma(gw, sDc, fma(cv, sDb, wxK * row_dot<P, J>(c_tab<P>.Ks, l[1])));
+            y[0] = fma(cv, sDa, wxK * row_dot<P, J>(tK, l[0]));
+            y[1] = fma(gw, sDc, fma(cv, sDb, wxK * row_dot<P, J>(tK, l[1])));
             y[2] = gw * sDb;
         }
     }
@@ -119,12 +148,12 @@ struct March {
     static __device__ __forceinline__ void finish(const MeshDev& g, const MarchArgs& A, int ix, int iy,
                                                   const double (&xp)[NOUT], const double (&yp)[NACC],
                                                   const double (&node)[NF], double wxA_line, double wyA) {
-        const size_t off = (size_t)ix * g.LD + iy;
+        const int off = ix * g.LD + iy;
         const int gix = g.gx0 + ix;
         // interface lines are duplicated on two ranks: the element sums of both ranks are added by the halo exchange,
         // pointwise terms and boundary rows are contributed by the owner only (the rank for which it is NOT the last line)
         const bool owner = !(g.has_right && ix == g.NX - 1);
-        if constexpr (MODE == MODE_K) {
+        if constexpr (MODE == MODE_K || MODE == MODE_DIV) {
             A.y0[off] = xp[0] + yp[0];
         } else if constexpr (MODE == MODE_G) {
             if (A.y0) A.y0[off] = xp[0];
@@ -165,14 +194,14 @@ struct March {
         static __device__ __forceinline__ void run(const MeshDev& g, const MarchArgs& A, int m, int iy, int t,
                                                    const double (&r)[NF][n], double cKx, double wyA, double cc,
                                                    const double (&xcarry)[NOUT], const double (&ycarry)[NACC],
-                                                   const double* __restrict__ sA, int pitch) {
+                                                   const double* __restrict__ sA, int pitch, int z) {
             if constexpr (I < P) {
                 const int ix = m * P + I;
-                const size_t off = (size_t)ix * g.LD + iy;
+                const int off = ix * g.LD + iy;
                 double Uc = 0.0;
                 if constexpr (NV) Uc = A.U[off];
                 double xp[NOUT], yp[NACC], node[NF];
-                xrow<I>(r, Uc, cKx, wyA, cc, xp);
+                xrow<I>(r, Uc, cKx, wyA, cc, xp, z);
                 if constexpr (I == 0) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) xp[o] += xcarry[o];
@@ -180,13 +209,13 @@ struct March {
                     for (int o = 0; o < NACC; ++o) yp[o] = ycarry[o];
                 } else {
 #pragma unroll
-                    for (int o = 0; o < NACC; ++o) yp[o] = sA[((size_t)o * P + (I - 1)) * pitch + t];
+                    for (int o = 0; o < NACC; ++o) yp[o] = sA[(o * P + (I - 1)) * pitch + t];
                 }
 #pragma unroll
                 for (int f = 0; f < NF; ++f) node[f] = r[f][I];
                 const double wxl = 0.5 * g.dx * asm_weight<P>(ix, g.nex);
                 finish(g, A, ix, iy, xp, yp, node, wxl, wyA);
-                RowLoop<I + 1>::run(g, A, m, iy, t, r, cKx, wyA, cc, xcarry, ycarry, sA, pitch);
+                RowLoop<I + 1>::run(g, A, m, iy, t, r, cKx, wyA, cc, xcarry, ycarry, sA, pitch, z);
             }
         }
     };
@@ -196,15 +225,15 @@ struct March {
         // rows J .. P-1 of one element line: write to the accumulators (colour phase 1); row P is returned in top[]
         static __device__ __forceinline__ void run(const double (&l)[NF][n], const double* __restrict__ sV, int col0,
                                                    double wxK, double wxA, double cc, double* __restrict__ sA,
-                                                   size_t accStride, double (&top)[NACC]) {
+                                                   int accStride, double (&top)[NACC], int z) {
             double Vc = 0.0;
             if constexpr (NV) Vc = sV[col0 + J];
             double y[NACC];
-            yrow<J>(l, Vc, wxK, wxA, cc, y);
+            yrow<J>(l, Vc, wxK, wxA, cc, y, z);
             if constexpr (J < P) {
 #pragma unroll
                 for (int o = 0; o < NACC; ++o) sA[o * accStride + col0 + J] = y[o];
-                YLoop<J + 1>::run(l, sV, col0, wxK, wxA, cc, sA, accStride, top);
+                YLoop<J + 1>::run(l, sV, col0, wxK, wxA, cc, sA, accStride, top, z);
             } else {
 #pragma unroll
                 for (int o = 0; o < NACC; ++o) top[o] = y[o];
@@ -216,7 +245,7 @@ struct March {
     template <bool FULL>
     static __device__ __forceinline__ void yphase(const MeshDev& g, const MarchArgs& A, int lineP, int nty, int halo,
                                                   bool last_strip, double* __restrict__ sU, double* __restrict__ sA,
-                                                  int pitch, double cc) {
+                                                  int pitch, double cc, int z) {
         const int q = threadIdx.x;
         const int nlines = FULL ? P : 1;
         const int nfull = nlines * nty;
@@ -229,8 +258,8 @@ struct March {
 #pragma unroll
         for (int o = 0; o < NACC; ++o) top[o] = 0.0;
         const int col0 = halo + nn * P;   // column of node j = 0 of element nn (halo element: column 0)
-        const size_t accStride = (size_t)P * pitch;
-        double* sAl = sA + (size_t)slot * pitch;
+        const int accStride = P * pitch;
+        double* sAl = sA + slot * pitch;
         if (full_item || halo_item) {
             const int ix = lineP - (P - 1) + slot;   // local line of this slot (slot P-1 <-> lineP)
             const double wxA = 0.5 * g.dx * asm_weight<P>(ix, g.nex);
@@ -239,14 +268,14 @@ struct March {
 #pragma unroll
             for (int f = 0; f < NF; ++f)
 #pragma unroll
-                for (int k = 0; k < n; ++k) l[f][k] = sU[((size_t)f * P + slot) * pitch + col0 + k];
-            const double* sV = sU + ((size_t)NF * P + slot) * pitch;
+                for (int k = 0; k < n; ++k) l[f][k] = sU[(f * P + slot) * pitch + col0 + k];
+            const double* sV = sU + (NF * P + slot) * pitch;
             if (full_item) {
-                YLoop<0>::run(l, sV, col0, wxK, wxA, cc, sAl, accStride, top);
+                YLoop<0>::run(l, sV, col0, wxK, wxA, cc, sAl, accStride, top, z);
             } else {
                 double Vc = 0.0;
                 if constexpr (NV) Vc = sV[col0 + P];
-                yrow<P>(l, Vc, wxK, wxA, cc, top);
+                yrow<P>(l, Vc, wxK, wxA, cc, top, z);
             }
         }
         __syncthreads();   // colour phase 2: every element adds its top row to the node it shares with the element above
@@ -269,14 +298,14 @@ struct March {
 };
 
 template <int P, int MODE>
-__global__ void __launch_bounds__(320) sem_march_kernel(const MeshDev g, const MarchArgs A, const int Ty,
+__global__ void __launch_bounds__(SEM_MARCH_MAXT, ModeTraits<MODE>::MINB) sem_march_kernel(const MeshDev g, const MarchArgs A, const int Ty,
                                                          const int Mx, const int pitch) {
     using MM = March<P, MODE>;
     constexpr int n = P + 1;
     constexpr int NF = MM::NF, NV = MM::NV, NACC = MM::NACC, NOUT = MM::NOUT;
     extern __shared__ double smem[];
     double* sU = smem;                                   // [NF+NV][P][pitch] staged node lines
-    double* sA = smem + (size_t)(NF + NV) * P * pitch;   // [NACC][P][pitch]  y-contraction accumulators
+    double* sA = smem + (NF + NV) * P * pitch;   // [NACC][P][pitch]  y-contraction accumulators
 
     const int n0 = blockIdx.x * Ty;
     const int nty = min(Ty, g.ney - n0);
@@ -302,61 +331,63 @@ __global__ void __launch_bounds__(320) sem_march_kernel(const MeshDev g, const M
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) xcarry[o] = 0.0;
 
+    const int z0 = opaque_zero(A.zero);
     // ---- prologue: line m0*P.  Its x-part from the element on the left (x-halo), its y-part from a 1-line y phase ----
     {
         const int ix = m0 * P;
         if (stage) {
-            const size_t off = (size_t)ix * g.LD + iy;
+            const int off = ix * g.LD + iy;
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 r[f][P] = fld[f][off];
-                sU[((size_t)f * P + (P - 1)) * pitch + t] = r[f][P];
+                sU[(f * P + (P - 1)) * pitch + t] = r[f][P];
             }
-            if constexpr (NV) sU[((size_t)NF * P + (P - 1)) * pitch + t] = A.V[off];
+            if constexpr (NV) sU[(NF * P + (P - 1)) * pitch + t] = A.V[off];
         }
         if (own && m0 > 0) {
 #pragma unroll
             for (int f = 0; f < NF; ++f)
 #pragma unroll
-                for (int k = 0; k < P; ++k) r[f][k] = fld[f][(size_t)(ix - P + k) * g.LD + iy];
+                for (int k = 0; k < P; ++k) r[f][k] = fld[f][(ix - P + k) * g.LD + iy];
             double Uc = 0.0;
-            if constexpr (NV) Uc = A.U[(size_t)ix * g.LD + iy];
-            MM::template xrow<P>(r, Uc, cKx, wyA, cc, xcarry);
+            if constexpr (NV) Uc = A.U[ix * g.LD + iy];
+            MM::template xrow<P>(r, Uc, cKx, wyA, cc, xcarry, z0);
         }
         __syncthreads();
-        MM::template yphase<false>(g, A, ix, nty, halo, last_strip, sU, sA, pitch, cc);
+        MM::template yphase<false>(g, A, ix, nty, halo, last_strip, sU, sA, pitch, cc, z0);
 #pragma unroll
-        for (int o = 0; o < NACC; ++o) ycarry[o] = own ? sA[((size_t)o * P + (P - 1)) * pitch + t] : 0.0;
+        for (int o = 0; o < NACC; ++o) ycarry[o] = own ? sA[(o * P + (P - 1)) * pitch + t] : 0.0;
     }
 
     // ---- march over the element columns of this chunk ------------------------------------------------------------------
     for (int m = m0; m < m1; ++m) {
         __syncthreads();   // accumulators / staged lines of the previous step are no longer read
+        const int z = opaque_zero(A.zero);
         if (stage) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) r[f][0] = r[f][P];
 #pragma unroll
             for (int k = 1; k <= P; ++k) {
-                const size_t off = (size_t)(m * P + k) * g.LD + iy;
+                const int off = (m * P + k) * g.LD + iy;
 #pragma unroll
                 for (int f = 0; f < NF; ++f) r[f][k] = fld[f][off];
             }
 #pragma unroll
             for (int k = 1; k <= P; ++k) {
 #pragma unroll
-                for (int f = 0; f < NF; ++f) sU[((size_t)f * P + (k - 1)) * pitch + t] = r[f][k];
-                if constexpr (NV) sU[((size_t)NF * P + (k - 1)) * pitch + t] = A.V[(size_t)(m * P + k) * g.LD + iy];
+                for (int f = 0; f < NF; ++f) sU[(f * P + (k - 1)) * pitch + t] = r[f][k];
+                if constexpr (NV) sU[(NF * P + (k - 1)) * pitch + t] = A.V[(m * P + k) * g.LD + iy];
             }
         }
         __syncthreads();
-        MM::template yphase<true>(g, A, m * P + P, nty, halo, last_strip, sU, sA, pitch, cc);
+        MM::template yphase<true>(g, A, m * P + P, nty, halo, last_strip, sU, sA, pitch, cc, z);
         if (own) {
-            MM::template RowLoop<0>::run(g, A, m, iy, t, r, cKx, wyA, cc, xcarry, ycarry, sA, pitch);
+            MM::template RowLoop<0>::run(g, A, m, iy, t, r, cKx, wyA, cc, xcarry, ycarry, sA, pitch, z);
             double Uc = 0.0;
-            if constexpr (NV) Uc = A.U[(size_t)(m * P + P) * g.LD + iy];
-            MM::template xrow<P>(r, Uc, cKx, wyA, cc, xcarry);
+            if constexpr (NV) Uc = A.U[(m * P + P) * g.LD + iy];
+            MM::template xrow<P>(r, Uc, cKx, wyA, cc, xcarry, z);
 #pragma unroll
-            for (int o = 0; o < NACC; ++o) ycarry[o] = sA[((size_t)o * P + (P - 1)) * pitch + t];
+            for (int o = 0; o < NACC; ++o) ycarry[o] = sA[(o * P + (P - 1)) * pitch + t];
         }
     }
 

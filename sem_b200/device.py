@@ -1,0 +1,140 @@
+"""Device-side mesh context: owns a ``sem_ctx`` (C ABI), allocates padded field vectors as torch tensors and moves
+the reference's dense numpy vectors across the host/device boundary.
+
+Layout: the reference stores a field as a 1-D array of length N with node (ix, iy) at ``iy + NY*ix`` (SEM.py:110).
+On the device the same field is a ``[NX, LD]`` fp64 tensor with ``LD = round_up(NY, 16)`` (zero pads) so that every
+node line starts 128-byte aligned.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import GLL
+from . import _lib as L
+
+
+def default_device():
+    """CUDA device ordinal of this process: SEM_B200_DEVICE, else LOCAL_RANK (torchrun), else 0."""
+    for key in ("SEM_B200_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+class SemDevice:
+    def __init__(self, P, N_ex, N_ey, dx, dy, device=None, m_begin=0, m_end=None):
+        if not torch.cuda.is_available():
+            raise L.SemError("sem_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = L.load()
+        self.P, self.N_ex, self.N_ey = int(P), int(N_ex), int(N_ey)
+        self.dx, self.dy = float(dx), float(dy)
+        self.device = default_device() if device is None else int(device)
+        self.m_begin = int(m_begin)
+        self.m_end = self.N_ex if m_end is None else int(m_end)
+        self.tdev = torch.device("cuda", self.device)
+        torch.cuda.set_device(self.tdev)
+        self._D = np.ascontiguousarray(GLL.standard_differentiation_matrix(self.P))
+        self._Ks = np.ascontiguousarray(GLL.standard_stiffness_matrix(self.P))
+        self._w = np.ascontiguousarray(GLL.standard_nodes(self.P)[1])
+        desc = L.sem_mesh_desc(self.P, self.N_ex, self.N_ey, self.dx, self.dy,
+                               self._D.ctypes.data, self._Ks.ctypes.data, self._w.ctypes.data,
+                               self.device, self.m_begin, self.m_end)
+        ctx = C.c_void_p()
+        L.check(self.lib.sem_ctx_create(C.byref(ctx), C.byref(desc)), "sem_ctx_create")
+        self.ctx = ctx
+        self.LD = self.lib.sem_ctx_ld(ctx)
+        self.NX = self.lib.sem_ctx_nx(ctx)
+        self.NY = self.lib.sem_ctx_ny(ctx)
+        self.vec_len = self.lib.sem_ctx_vec_len(ctx)
+        self.N_local = self.NX * self.NY
+        self._pinned = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.sem_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ---- storage -------------------------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def zeros(self, k=None):
+        shape = (self.NX, self.LD) if k is None else (k, self.NX, self.LD)
+        return torch.zeros(shape, dtype=torch.float64, device=self.tdev)
+
+    def set_tiling(self, Ty=0, Mx=0):
+        L.check(self.lib.sem_ctx_set_tiling(self.ctx, int(Ty), int(Mx)), "sem_ctx_set_tiling")
+
+    def _host(self, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        if a.size != self.N_local:
+            raise ValueError(f"expected a vector of length {self.N_local}, got {a.size}")
+        return a
+
+    def to_device(self, arr, out=None):
+        """numpy (N,) -> padded device vector (pads untouched, i.e. zero)."""
+        a = self._host(arr)
+        if out is None:
+            out = self.zeros()
+        L.check(self.lib.sem_h2d(self.ctx, a.ctypes.data, out.data_ptr(), self.stream), "sem_h2d")
+        # the async copy reads pageable host memory: make sure it is done before `a` can be released
+        torch.cuda.current_stream(self.tdev).synchronize()
+        return out
+
+    def to_host(self, vec, out=None):
+        """padded device vector -> fresh numpy (N,) (synchronises)."""
+        if out is None:
+            out = np.empty(self.N_local, dtype=np.float64)
+        L.check(self.lib.sem_d2h(self.ctx, vec.data_ptr(), out.ctypes.data, self.stream), "sem_d2h")
+        return out
+
+    # ---- single operators ------------------------------------------------------------------------------------------
+    def apply_stiffness(self, x, y):
+        L.check(self.lib.sem_apply_stiffness(self.ctx, x.data_ptr(), y.data_ptr(), self.stream), "sem_apply_stiffness")
+        return y
+
+    def apply_gradient(self, x, gx, gy, scale=1.0):
+        L.check(self.lib.sem_apply_gradient(self.ctx, x.data_ptr(), float(scale),
+                                            gx.data_ptr() if gx is not None else None,
+                                            gy.data_ptr() if gy is not None else None, self.stream),
+                "sem_apply_gradient")
+        return gx, gy
+
+    def apply_mass(self, x, y):
+        L.check(self.lib.sem_apply_mass(self.ctx, x.data_ptr(), y.data_ptr(), self.stream), "sem_apply_mass")
+        return y
+
+    def mass_diag(self, m=None):
+        m = self.zeros() if m is None else m
+        L.check(self.lib.sem_mass_diag(self.ctx, m.data_ptr(), self.stream), "sem_mass_diag")
+        return m
+
+    def gather_scatter(self, elem, y=None):
+        """Colour-ordered assembly of a device element array [m, n, i, j] into a padded vector."""
+        y = self.zeros() if y is None else y
+        L.check(self.lib.sem_gather_scatter(self.ctx, elem.data_ptr(), y.data_ptr(), self.stream), "sem_gather_scatter")
+        return y
+
+    def scatter(self, x, elem=None):
+        if elem is None:
+            elem = torch.empty((self.m_end - self.m_begin, self.N_ey, self.P + 1, self.P + 1), dtype=torch.float64,
+                               device=self.tdev)
+        L.check(self.lib.sem_scatter(self.ctx, x.data_ptr(), elem.data_ptr(), self.stream), "sem_scatter")
+        return elem
+
+    def dot(self, x, y):
+        out = C.c_double()
+        L.check(self.lib.sem_dot(self.ctx, x.data_ptr(), y.data_ptr(), x.numel(), C.byref(out), self.stream), "sem_dot")
+        return out.value
+
+    def axpby(self, a, x, b, y):
+        """y = a*x + b*y on the device (own kernel)."""
+        L.check(self.lib.sem_axpby(self.ctx, float(a), x.data_ptr(), float(b), y.data_ptr(), x.numel(), self.stream),
+                "sem_axpby")
+        return y

@@ -1,0 +1,239 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes numpy -> Python drop-in class -> ctypes ->
+C ABI -> sm_100a kernels.  Checked against (1) the committed outputs of the unmodified reference (tests/golden) and
+(2) the CPU oracle on seeded inputs.  Tolerances: operator applies <= 1e-12 relative L2 (north_star), converged
+fields <= 1e-8 relative L2 (pressure on the C3 mesh: 2e-7, the reference's own convergence floor there)."""
+import numpy as np
+import pytest
+
+from tests.conftest import relerr
+from tests.golden.make_golden_cases import CD_CASES, MESHES, NS_CASES
+
+pytestmark = pytest.mark.gpu
+
+APPLY_TOL = 1e-12
+FIELD_TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def sem():
+    import sem_b200
+    return sem_b200
+
+
+def _dev(sem, P, nx, ny, Lx=1.0, Ly=1.0):
+    return sem.SemDevice(P, nx, ny, Lx / nx, Ly / ny)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,P,nx,ny,Lx,Ly", MESHES)
+def test_operators_match_reference(sem, golden, tag, P, nx, ny, Lx, Ly):
+    g = golden("operators")
+    d = _dev(sem, P, nx, ny, Lx, Ly)
+    x = d.to_device(g[f"{tag}/x"])
+    y, y2 = d.zeros(), d.zeros()
+    assert relerr(d.to_host(d.apply_stiffness(x, y)), g[f"{tag}/Kx"]) < APPLY_TOL
+    d.apply_gradient(x, y, y2)
+    assert relerr(d.to_host(y), g[f"{tag}/Gxx"]) < APPLY_TOL
+    assert relerr(d.to_host(y2), g[f"{tag}/Gyx"]) < APPLY_TOL
+    assert relerr(d.to_host(d.apply_mass(x, y)), g[f"{tag}/Mx"]) < APPLY_TOL
+    assert relerr(d.to_host(d.mass_diag()), g[f"{tag}/Mdiag"]) < APPLY_TOL
+    # pads stay zero
+    assert float(y[:, d.NY:].abs().max()) == 0.0 if d.LD > d.NY else True
+
+
+@pytest.mark.parametrize("tag,P,nx,ny,Lx,Ly", MESHES)
+def test_gather_scatter_and_interpolation(sem, golden, tag, P, nx, ny, Lx, Ly):
+    g = golden("operators")
+    SEM = sem.SEM
+    a1 = SEM.assemble(g[f"{tag}/A_e"])
+    assert relerr(a1, g[f"{tag}/assembled"]) < 1e-15
+    assert np.array_equal(a1, SEM.assemble(g[f"{tag}/A_e"]))          # bitwise reproducible
+    assert np.array_equal(SEM.scatter(g[f"{tag}/x"], P, nx, ny), g[f"{tag}/scattered"])
+    pts_e = SEM.element_nodes(P, nx, ny, Lx / nx, Ly / ny)
+    val = SEM.eval_interpolation(g[f"{tag}/scattered"], pts_e, (g[f"{tag}/xp"], g[f"{tag}/yp"]))
+    assert relerr(val, g[f"{tag}/interp"]) < 1e-13
+    K = SEM.global_stiffness_matrix(P, nx, ny, Lx / nx, Ly / ny)
+    assert relerr(K @ g[f"{tag}/x"], g[f"{tag}/Kx"]) < APPLY_TOL
+
+
+@pytest.mark.parametrize("P", list(range(1, 17)))
+@pytest.mark.parametrize("tiling", [(0, 0), (1, 1), (2, 3)])
+def test_all_orders_and_tilings_against_oracle(sem, P, tiling):
+    """Every polynomial order, with strip/chunk sizes that force the y-halo and x-halo paths."""
+    from oracle import sem_oracle as so
+    nx, ny, Lx, Ly = 5, 4, 1.3, 0.9
+    if P >= 12:
+        nx, ny = 3, 3
+    M, K, Gx, Gy = so.global_operators(P, nx, ny, Lx / nx, Ly / ny)
+    rng = np.random.default_rng(1000 + P)
+    xh = rng.standard_normal(M.size)
+    d = _dev(sem, P, nx, ny, Lx, Ly)
+    d.set_tiling(*tiling)
+    x = d.to_device(xh)
+    y, y2 = d.zeros(), d.zeros()
+    assert relerr(d.to_host(d.apply_stiffness(x, y)), K @ xh) < APPLY_TOL
+    d.apply_gradient(x, y, y2, scale=2.5)
+    assert relerr(d.to_host(y), 2.5 * (Gx @ xh)) < APPLY_TOL
+    assert relerr(d.to_host(y2), 2.5 * (Gy @ xh)) < APPLY_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,kw", CD_CASES)
+def test_cd_matches_reference(sem, golden, tag, kw):
+    g = golden("cd")
+    k = lambda s: g[f"{tag}/{s}"]
+    cd = sem.ConvectionDiffusionSolver(mtol=1e-13, **kw)
+    assert cd.N == k("T").size
+    assert relerr(cd._get_residuals(k("T"), k("ur"), k("vr")), k("res_r")) < APPLY_TOL
+    cd._calc_jacobians(k("T"))
+    assert relerr(cd._get_dresiduals(k("dT")), k("dres_r")) < APPLY_TOL
+    assert relerr(cd._get_dresiduals(k("dT"), k("du"), k("dv")), k("dres_r_uv")) < APPLY_TOL
+    assert relerr(cd._get_dresiduals(k("dT"), du=k("du")), k("dres_r_u")) < APPLY_TOL
+    assert relerr(cd._get_residuals(k("T"), k("u"), k("v")), k("res")) < APPLY_TOL
+    assert relerr(cd._get_dresiduals(k("dT")), k("dres")) < APPLY_TOL
+    T = cd._get_solution(k("u"), k("v"))
+    assert relerr(T, k("T_sol")) < FIELD_TOL
+    cd._get_residuals(k("T"), k("u"), k("v"))
+    assert relerr(cd._get_update(k("rhs")), k("dT_sol")) < FIELD_TOL
+    # warm start from the answer converges immediately and returns it
+    assert relerr(cd._get_solution(k("u"), k("v"), T0=T), k("T_sol")) < FIELD_TOL
+    with pytest.raises(ValueError):
+        cd._get_residuals(k("T")[:-1], k("u"), k("v"))
+
+
+@pytest.mark.parametrize("tiling", [(1, 1), (3, 2)])
+def test_cd_tilings(sem, golden, tiling):
+    g = golden("cd")
+    tag, kw = CD_CASES[1]
+    k = lambda s: g[f"{tag}/{s}"]
+    cd = sem.ConvectionDiffusionSolver(mtol=1e-13, **kw)
+    cd._dev.set_tiling(*tiling)
+    assert relerr(cd._get_residuals(k("T"), k("ur"), k("vr")), k("res_r")) < APPLY_TOL
+    cd._calc_jacobians(k("T"))
+    assert relerr(cd._get_dresiduals(k("dT"), k("du"), k("dv")), k("dres_r_uv")) < APPLY_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,kw,solve", NS_CASES)
+def test_ns_applies_match_reference(sem, golden, tag, kw, solve):
+    g = golden("ns")
+    k = lambda s: g[f"{tag}/{s}"]
+    ns = sem.NavierStokesSolver(mtol=1e-13, mtol_newton=1e-13, iprint=[], **kw)
+    for tiling in [(0, 0), (1, 2)]:
+        ns._dev.set_tiling(*tiling)
+        ru, rv, rc = ns._get_residuals(k("u"), k("v"), k("p"), k("T"))
+        assert relerr(ru, k("res_u")) < APPLY_TOL and relerr(rv, k("res_v")) < APPLY_TOL
+        assert relerr(rc, k("res_c")) < APPLY_TOL
+        ns._calc_jacobians(k("u"), k("v"))
+        a, b, c = ns._get_dresiduals(k("du"), k("dv"), k("dp"))
+        assert relerr(a, k("dres_u")) < APPLY_TOL and relerr(b, k("dres_v")) < APPLY_TOL
+        assert relerr(c, k("dres_c")) < APPLY_TOL
+        a, b, c = ns._get_dresiduals(k("du"), k("dv"), k("dp"), k("dT"))
+        assert relerr(a, k("dresT_u")) < APPLY_TOL and relerr(b, k("dresT_v")) < APPLY_TOL
+        assert relerr(c, k("dresT_c")) < APPLY_TOL
+
+
+@pytest.mark.parametrize("tag,kw,solve", [c for c in NS_CASES if c[2]])
+def test_ns_solution_matches_reference(sem, golden, tag, kw, solve):
+    g = golden("ns")
+    k = lambda s: g[f"{tag}/{s}"]
+    ns = sem.NavierStokesSolver(mtol=1e-13, mtol_newton=1e-13, iprint=[], **kw)
+    u0, v0, p0 = (np.zeros(ns.N) for _ in range(3))
+    u, v, p = ns._get_solution(k("T_in"), u0=u0, v0=v0, p0=p0)
+    assert u is u0 and v is v0 and p is p0                       # in-place contract of NS:248-267
+    ptol = 2e-7 if tag == "c3" else FIELD_TOL                    # see tests/test_oracle.py
+    assert relerr(u, k("u_sol")) < FIELD_TOL and relerr(v, k("v_sol")) < FIELD_TOL
+    assert relerr(p, k("p_sol")) < ptol
+    assert ns._k == int(k("newton_its"))
+    # linear update about the converged state (reference solved it to mtol = 1e-11 only)
+    ns._get_residuals(k("u_sol"), k("v_sol"), k("p_sol"), k("T_in"))
+    ns._calc_jacobians(k("u_sol"), k("v_sol"))
+    ns._mtol = 1e-11
+    a, b, c = ns._get_update(k("rhs_u"), k("rhs_v"), k("rhs_c"))
+    assert relerr(a, k("upd_u")) < 1e-7 and relerr(b, k("upd_v")) < 1e-7 and relerr(c, k("upd_p")) < 1e-5
+
+
+def test_ns_constructor_errors(sem):
+    with pytest.raises(ValueError, match="Cannot have Re == 0 and Gr != 0"):
+        sem.NavierStokesSolver(1, 1, 0, 1.0, 2, 2, 2)
+
+
+def test_boussinesq_fixed_point_block_gauss_seidel(sem, golden):
+    """C3 physics: block Gauss-Seidel over the GPU solvers (solve_nonlinear semantics of the two OpenMDAO components)
+    reaches the same coupled state as the same loop over the reference's solvers."""
+    g = golden("boussinesq_c3")
+    Re, Ra, Pr = 1e3, 1e3, 0.71
+    cd = sem.ConvectionDiffusionSolver(1., 1., Re * Pr, 4, 8, 8, T_W=0.5, T_E=-0.5, mtol=1e-13)
+    ns = sem.NavierStokesSolver(1., 1., Re, Ra / Pr, 4, 8, 8, mtol=1e-13, mtol_newton=1e-13, iprint=[])
+    N = cd.N
+    T, u, v, p = (np.zeros(N) for _ in range(4))
+    for sweep in range(60):
+        T = cd._get_solution(u, v, T0=T)
+        u, v, p = ns._get_solution(T, u0=u, v0=v, p0=p)
+        r = np.hstack((cd._get_residuals(T, u, v),) + ns._get_residuals(u, v, p, T))
+        if np.linalg.norm(r) <= 1e-11 * np.sqrt(4 * N):
+            break
+    assert sweep + 1 == int(g["sweeps"])
+    assert relerr(T, g["T"]) < FIELD_TOL and relerr(u, g["u"]) < 1e-7 and relerr(v, g["v"]) < 1e-7
+    xp, yp = np.meshgrid(np.linspace(0, 1, 101), np.linspace(0, 1, 101), indexing='ij')
+    up = ns._get_interpol(u, (xp, yp))
+    assert abs(up.max() * Re * Pr - float(g["umax_RePr"])) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_mid_size_against_oracle(sem):
+    """64 x 48 elements, P = 8 (197k nodes): full tiles, many strips and chunks, against the oracle's CSR."""
+    from oracle import sem_oracle as so
+    P, nx, ny = 8, 64, 48
+    cd_o = so.CDOracle(1.0, 1.0, 40.0, P, nx, ny, T_W=0.5, T_E=-0.5)
+    rng = np.random.default_rng(7)
+    T, u, v, dT = (rng.standard_normal(cd_o.N) for _ in range(4))
+    cd = sem.ConvectionDiffusionSolver(1.0, 1.0, 40.0, P, nx, ny, T_W=0.5, T_E=-0.5)
+    assert relerr(cd._get_residuals(T, u, v), cd_o._get_residuals(T, u, v)) < APPLY_TOL
+    assert relerr(cd._get_dresiduals(dT), cd_o._get_dresiduals(dT)) < APPLY_TOL
+    ns_o = so.NSOracle(1.0, 1.0, 400.0, 10.0, P, nx, ny, u_N=1.0)
+    ns = sem.NavierStokesSolver(1.0, 1.0, 400.0, 10.0, P, nx, ny, u_N=1.0, iprint=[])
+    p = rng.standard_normal(cd_o.N)
+    for a, b in zip(ns._get_residuals(u, v, p, T), ns_o._get_residuals(u, v, p, T)):
+        assert relerr(a, b) < APPLY_TOL
+    ns._calc_jacobians(u, v)
+    ns_o._calc_jacobians(u, v)
+    for a, b in zip(ns._get_dresiduals(dT, T, p, u), ns_o._get_dresiduals(dT, T, p, u)):
+        assert relerr(a, b) < APPLY_TOL
+
+
+def test_full_size_properties(sem):
+    """BASELINE config 5 (1024 x 1024 elements, P = 8, 67.1M nodes): size-independent properties of the fused apply."""
+    import torch
+    P, ne = 8, 1024
+    d = sem.SemDevice(P, ne, ne, 1.0 / ne, 1.0 / ne)
+    gen = torch.Generator(device=d.tdev).manual_seed(0)
+    x, y = d.zeros(), d.zeros()
+    x[:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
+    y[:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
+    Kx, Ky, one = d.zeros(), d.zeros(), d.zeros()
+    one[:, :d.NY] = 1.0
+    d.apply_stiffness(x, Kx)
+    d.apply_stiffness(y, Ky)
+    # symmetry  <y, K x> = <x, K y>,  null space K 1 = 0,  positive semi-definiteness
+    a, b = d.dot(y, Kx), d.dot(x, Ky)
+    assert abs(a - b) <= 1e-12 * max(abs(a), abs(b))
+    K1 = d.zeros()
+    d.apply_stiffness(one, K1)
+    assert np.sqrt(d.dot(K1, K1)) <= 1e-10 * np.sqrt(d.dot(Kx, Kx))
+    assert d.dot(x, Kx) > 0
+    # mass: sum(diag M) = area;  G_x 1 = 0 away from the W/E walls: <1, G_x x> = boundary flux of x
+    m = d.mass_diag()
+    assert abs(d.dot(m, one) - 1.0) < 1e-12
+    # run-to-run bitwise reproducibility of the fused gather-scatter
+    Kx2 = d.zeros()
+    d.apply_stiffness(x, Kx2)
+    assert torch.equal(Kx, Kx2)
+    # linearity
+    z, Kz = d.zeros(), d.zeros()
+    d.axpby(1.0, x, 0.0, z)
+    d.axpby(-2.0, y, 1.0, z)
+    d.apply_stiffness(z, Kz)
+    d.axpby(-1.0, Kx, 1.0, Kz)
+    d.axpby(2.0, Ky, 1.0, Kz)
+    assert np.sqrt(d.dot(Kz, Kz)) <= 1e-12 * np.sqrt(d.dot(Kx, Kx))

@@ -1,0 +1,75 @@
+"""CPU: host-side logic of the product and the C ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, relerr
+from tests.golden.make_golden_cases import MESHES
+
+
+def test_library_exports_every_declared_symbol():
+    """libsem_b200.so loads and exports exactly the entry points include/sem_b200.h declares."""
+    from sem_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "sem_b200.h")).read()
+    declared = set(re.findall(r"\b(sem_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found in the header"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in sem_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
+    assert _lib.load().sem_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product raises instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import sem_b200
+    from sem_b200._lib import SemError
+    with pytest.raises(SemError):
+        sem_b200.ConvectionDiffusionSolver(1, 1, 40, 4, 4, 4)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sem_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU oracle", ""), f"{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16])
+def test_host_gll_matches_reference(golden, P):
+    from sem_b200 import GLL
+    g = golden("gll")
+    x, w, _ = GLL.standard_nodes(P)
+    assert np.array_equal(x, g[f"x{P}"]) and np.array_equal(w, g[f"w{P}"])
+    assert np.array_equal(GLL.standard_differentiation_matrix(P), g[f"D{P}"])
+    assert np.array_equal(GLL.standard_stiffness_matrix(P), g[f"K{P}"])
+    assert np.array_equal(GLL.standard_gradient_matrix(P), g[f"G{P}"])
+    assert np.array_equal(GLL.standard_mass_matrix(P), np.diag(g[f"w{P}"]))
+    assert np.allclose(GLL.standard_evaluation_matrix(P, np.linspace(-1, 1, 7)), g[f"S{P}"], rtol=0, atol=1e-13)
+    F, Cm = GLL.standard_product_matrix(P), GLL.standard_convection_matrix(P)
+    assert np.array_equal(np.einsum('iii->i', F), w) and abs(F.sum() - w.sum()) < 1e-15
+    assert np.array_equal(np.einsum('iik->ik', Cm), g[f"G{P}"])
+
+
+@pytest.mark.parametrize("tag,P,nx,ny,Lx,Ly", MESHES)
+def test_host_mesh_functions_match_reference(golden, tag, P, nx, ny, Lx, Ly):
+    from sem_b200 import SEM
+    g = golden("operators")
+    assert np.array_equal(SEM.global_nodes(P, nx, ny, Lx / nx, Ly / ny), g[f"{tag}/points"])
+    pts_e = SEM.element_nodes(P, nx, ny, Lx / nx, Ly / ny)
+    val = SEM.eval_interpolation(g[f"{tag}/scattered"], pts_e, (g[f"{tag}/xp"], g[f"{tag}/yp"]))
+    assert relerr(val, g[f"{tag}/interp"]) < 1e-13
+    assert SEM.global_index(P, nx, ny, nx - 1, ny - 1, P, P) == (nx * P + 1) * (ny * P + 1) - 1
+    with pytest.raises(ValueError):
+        SEM.global_index(P, nx, ny, nx, 0, 0, 0)
+    with pytest.raises(ValueError):
+        SEM.xi2x(0, np.array([1.5]), 1.0)
+    e, xi = SEM.x2xi(np.array([0.0, Lx / nx, Lx]), Lx / nx)
+    assert list(e) == [0, 0, nx - 1] and np.allclose(xi, [-1, 1, 1])
