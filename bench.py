@@ -1,0 +1,329 @@
+"""bench.py -- headline benchmark of the sem_b200 hot path (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): "GDOF/s element apply".  One step = one fused matrix-free application of the convection-
+diffusion Jacobian (`ConvectionDiffusionSolver._get_dresiduals`, reference CD:104-121: K + Pe(diag(u)G_x + diag(v)G_y)
+with Dirichlet rows) on BASELINE config 5: synthetic mesh of 1024 x 1024 elements, P = 8, 67.1M nodes per field.
+`value` = nodes processed by all ranks / device time with inputs resident in HBM; `e2e` = the same apply through the
+public Python class with pinned HOST buffers (H2D of the input field and D2H of the result inside the timed region).
+For N > 1 the element columns are partitioned across the ranks (strong scaling of the fixed config-5 mesh) with an
+NCCL exchange of the interface node lines.
+
+`--impl reference` times the reference's own CPU implementation of this apply -- scipy CSR mat-vec on the host, on
+matrices value-identical to the reference's (oracle port, the reference itself cannot build this mesh: SURVEY 8c) --
+on a bounded sample mesh.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "GDOF/s element apply (CD Jacobian-vector product, reference CD:104-121)"
+UNIT = "GDOF/s"
+P_ORDER = 8
+NE = 1024                 # config 5: 1024 x 1024 elements
+PE = 40.0
+CPU_SAMPLE_NE = 128       # bounded CPU sample: 128 x 128 elements, P = 8 (1.05M nodes)
+ALG_BYTES_PER_NODE = 32   # fp64: read dT, u, v, write dres
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_apply_sample(steps, warmup):
+    """The reference's CPU path for this apply: CSR mat-vec + Dirichlet rows (CD:112-119) on the sample mesh."""
+    import numpy as np
+    from oracle import sem_oracle as so
+    ne = CPU_SAMPLE_NE
+    cd = so.CDOracle(1.0, 1.0, PE, P_ORDER, ne, ne, T_W=0.5, T_E=-0.5)
+    u = cd._get_vector(lambda x, y: y - 0.5)
+    v = cd._get_vector(lambda x, y: 0.5 - x)
+    rng = np.random.default_rng(0)
+    dT = rng.standard_normal(cd.N)
+    cd._get_residuals(dT, u, v)          # builds Sys like the reference (outside the timed region)
+    for _ in range(warmup):
+        cd._get_dresiduals(dT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cd._get_dresiduals(dT)
+    dt = (time.perf_counter() - t0) / steps
+    return cd.N / dt / 1e9, dt, cd.N
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(args.steps, 20)
+    val, dt, n = cpu_apply_sample(steps, max(args.warmup, 3))
+    cores = len(os.sched_getaffinity(0))
+    sample = f"{CPU_SAMPLE_NE}x{CPU_SAMPLE_NE} elements, P={P_ORDER} ({n} nodes), scipy CSR mat-vec, {steps} applies"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(), "note": "CPU arm runs the bounded sample mesh: " + sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores_available": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name():
+    return (f"BASELINE config 5: synthetic {NE}x{NE} elements, P={P_ORDER} ({(NE * P_ORDER + 1) ** 2} nodes/field), "
+            f"fused CD Jacobian-vector apply, Pe={PE:g}, Dirichlet W/E; inputs (1.6 GB) larger than L2")
+
+
+def run_ours(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sem_b200
+    from sem_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    cd = sem_b200.ConvectionDiffusionSolver(1.0, 1.0, PE, P_ORDER, NE, NE, T_W=0.5, T_E=-0.5, device=local,
+                                            **({"partition": (rank, world)} if world > 1 else {}))
+    d = cd._dev
+    n_local = d.NX * d.NY
+    n_global = (NE * P_ORDER + 1) ** 2
+    gen = torch.Generator(device=d.tdev).manual_seed(rank)
+
+    def rnd():
+        x = d.zeros()
+        x[:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
+        return x
+
+    dT, out = rnd(), d.zeros()
+    cd._u.copy_(rnd())
+    cd._v.copy_(rnd())
+    cd._have_sys = True
+    st = cd._state(with_jac=False)
+    lib = d.lib
+
+    def step():
+        L.check(lib.sem_cd_jvp(d.ctx, C.byref(st), dT.data_ptr(), None, None, out.data_ptr(), d.stream), "sem_cd_jvp")
+        if world > 1:
+            cd._exchange(out)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    # a short run leaves the sampler without a sample under load: keep the load up until it has a few
+    if sampler:
+        t_end = time.time() + 1.5
+        while len(sampler.rows) < 5 and time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=d.tdev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / steps
+    value = n_global / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the public class with pinned host buffers ------------------------------------------------------
+    e2e_steps = max(2, min(steps, 5))
+    host_in = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
+    host_in[:] = np.random.default_rng(rank).standard_normal(n_local)
+    cd._get_dresiduals(host_in)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res_host = cd._get_dresiduals(host_in)
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=d.tdev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.isfinite(res_host).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    achieved = ALG_BYTES_PER_NODE * n_local / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get("cd_jvp_dram_bytes_per_launch")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(), "partition": f"{world} strips of element columns" if world > 1 else "none",
+                   "l2": "inputs larger than L2 (3 x 537 MB read per step)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "sem_march_kernel<8, MODE_CD>", "peak_source": peak_src,
+                     "algorithmic_bytes_per_node": ALG_BYTES_PER_NODE, "nodes_per_launch": n_local},
+        "e2e": {"value": n_global / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 8),
+                "d2h_bytes_per_step": int(n_local * 8), "ms_per_step": e2e_s * 1e3,
+                "api": "ConvectionDiffusionSolver._get_dresiduals(numpy pinned) -> numpy"},
+        "gpu_launches": steps,
+        "clocks": clocks,
+    }
+    if world == 1:
+        cval, cdt, cn = cpu_apply_sample(20, 3)
+        line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": 1,
+                                "host_cores_available": len(os.sched_getaffinity(0)), "kind": "port",
+                                "sample": f"{CPU_SAMPLE_NE}x{CPU_SAMPLE_NE} elements, P={P_ORDER} ({cn} nodes), scipy CSR "
+                                          f"mat-vec of the reference-identical Sys matrix, 20 applies, {cdt * 1e3:.1f} ms each"}
+        if not args.no_extra:
+            line["extra"] = extra_numbers(sem_b200, d, lib, cd, st)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_numbers(sem_b200, d, lib, cd, st):
+    """Secondary numbers of the same run (not the headline): the other fused applies and one steady NS solve."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from sem_b200 import _lib as L
+    out = {}
+    peak, _ = measured_peaks()
+    n = d.NX * d.NY
+
+    def timeit(fn, k=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / k
+
+    x, y = cd._buf[0], cd._buf[1]
+    t = timeit(lambda: d.apply_stiffness(x, y))
+    out["stiffness_apply"] = {"gdof_s": n / t / 1e6, "hbm_frac": 16 * n / t / 1e6 / peak, "ms": t, "bytes_per_node": 16}
+    del cd
+    torch.cuda.empty_cache()
+    ns = sem_b200.NavierStokesSolver(1.0, 1.0, 400.0, 0.0, P_ORDER, NE, NE, u_N=1.0, iprint=[], device=d.device)
+    gen = torch.Generator(device=d.tdev).manual_seed(1)
+    for k in range(3):
+        ns._in[k][:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
+    ns._uv.copy_(ns._in[:2])
+    ns._have_sys = True
+    ns._jacobians_dev(ns._in[0], ns._in[1])
+    nst = ns._state()
+    nd = ns._dev
+    t = timeit(lambda: L.check(lib.sem_ns_jvp(nd.ctx, C.byref(nst), ns._in[0].data_ptr(), ns._in[1].data_ptr(),
+                                              ns._in[2].data_ptr(), None, ns._out[0].data_ptr(), ns._out[1].data_ptr(),
+                                              ns._out[2].data_ptr(), nd.stream), "sem_ns_jvp"), k=5)
+    out["ns_jvp_apply"] = {"gdof_s": 3 * n / t / 1e6, "hbm_frac": 96 * n / t / 1e6 / peak, "ms": t, "bytes_per_node": 96}
+    del ns
+    torch.cuda.empty_cache()
+    # steady NS solve, BASELINE config 2 (Examples/NavierStokes_Example.py: P=4, 16x16, Re=400, lid u_N=1), default tolerances
+    ns2 = sem_b200.NavierStokesSolver(1, 1, 400, 0, 4, 16, 16, u_N=1, iprint=[], device=d.device)
+    T0 = np.zeros(ns2.N)
+    ns2._get_solution(T0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ns2._get_solution(T0)
+    torch.cuda.synchronize()
+    out["ns_solve_config2"] = {"wall_s": time.perf_counter() - t0, "newton_its": ns2._k,
+                               "krylov_its": ns2.krylov_iters[-ns2._k:], "tolerances": "reference defaults (1e-7 / 1e-5)",
+                               "reference_cpu_wall_s_probe": 21.9, "reference_probe_source": "BASELINE.md section 2"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="headline only (used for the ncu captures)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
