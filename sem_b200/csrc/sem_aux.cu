@@ -133,6 +133,33 @@ int aux_neumann_rows(const MeshDev& g, TabDev t, const double* c, double* y, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// dense <-> padded repacking
+// ---------------------------------------------------------------------------------------------------------------
+template <bool PAD>
+__global__ void k_repack(const MeshDev g, const double* __restrict__ src, double* __restrict__ dst) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = (long long)g.NX * g.NY;
+    if (idx >= tot) return;
+    const long long ix = idx / g.NY, iy = idx % g.NY;
+    if (PAD) dst[ix * g.LD + iy] = src[idx];
+    else dst[idx] = src[ix * g.LD + iy];
+}
+
+int aux_pad(const MeshDev& g, const double* dense, double* vec, cudaStream_t st) {
+    const long long tot = (long long)g.NX * g.NY;
+    k_repack<true><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, dense, vec);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int aux_unpad(const MeshDev& g, const double* vec, double* dense, cudaStream_t st) {
+    const long long tot = (long long)g.NX * g.NY;
+    k_repack<false><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, vec, dense);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // standalone gather-scatter (SEM.assemble for 4-index arrays, SEM.py:126-131) -- colour ordered.
 // Elements are 4-coloured by the parity of (m, n); elements of one colour share no node, so each colour pass is a
 // plain read-modify-write without atomics and the four passes run in a fixed order: the sum at every shared node

@@ -21,6 +21,10 @@ int aux_stiffness_diag(const MeshDev& g, TabDev t, double* d, cudaStream_t st);
 int aux_neumann_rows(const MeshDev& g, TabDev t, const double* c, double* y, int pin_gx, int pin_iy, int skip_pin,
                      cudaStream_t st);
 
+// dense [NX][NY] <-> padded [NX][LD] repacking on the device (host copies stay 1-D and run at full PCIe rate)
+int aux_pad(const MeshDev& g, const double* dense, double* vec, cudaStream_t st);
+int aux_unpad(const MeshDev& g, const double* vec, double* dense, cudaStream_t st);
+
 // SEM.assemble (4-index) / SEM.scatter, element array [m][n][i][j]
 int aux_gather_scatter(const MeshDev& g, const double* elem, double* y, cudaStream_t st);
 int aux_scatter(const MeshDev& g, const double* x, double* elem, cudaStream_t st);

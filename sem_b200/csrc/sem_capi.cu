@@ -35,6 +35,7 @@ struct sem_ctx {
     int pin_gx, pin_iy;
     double *dD, *dKs, *dw;   // plain device tables
     double* dKdiag;          // diag(K), built on first use
+    double* dStage;          // dense [NX][NY] staging buffer of the host<->device boundary, built on first use
     RedScratch rs;
     double* d_small;         // device staging for reduction results
     double* h_small;         // pinned mirror
@@ -112,6 +113,7 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->dD); cudaFree(c->dKs); cudaFree(c->dw);
     if (c->dKdiag) cudaFree(c->dKdiag);
+    if (c->dStage) cudaFree(c->dStage);
     cudaFree(c->rs.partials); cudaFree(c->rs.counter);
     cudaFree(c->d_small); cudaFreeHost(c->h_small);
     delete c;
@@ -128,20 +130,31 @@ extern "C" int sem_ctx_set_tiling(sem_ctx* c, int Ty, int Mx) {
     return 0;
 }
 
+static int ensure_stage(sem_ctx* c) {
+    if (c->dStage) return 0;
+    SEM_CUDA(cudaMalloc(&c->dStage, sizeof(double) * (size_t)c->g.NX * c->g.NY));
+    return 0;
+}
+
+// One contiguous copy over PCIe (full rate from pinned memory) + a device repack kernel; a strided 2-D copy of
+// 8193-double rows runs at a fraction of the link rate.
 extern "C" int sem_h2d(sem_ctx* c, const double* host, double* vec, void* stream) {
     SEM_CHECK_CTX(c);
     const MeshDev& g = c->g;
-    SEM_CUDA(cudaMemcpy2DAsync(vec, sizeof(double) * g.LD, host, sizeof(double) * g.NY, sizeof(double) * g.NY, g.NX,
-                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ensure_stage(c)) return -1;
+    SEM_CUDA(cudaMemcpyAsync(c->dStage, host, sizeof(double) * (size_t)g.NX * g.NY, cudaMemcpyHostToDevice, st));
+    return aux_pad(g, c->dStage, vec, st);
 }
 
 extern "C" int sem_d2h(sem_ctx* c, const double* vec, double* host, void* stream) {
     SEM_CHECK_CTX(c);
     const MeshDev& g = c->g;
-    SEM_CUDA(cudaMemcpy2DAsync(host, sizeof(double) * g.NY, vec, sizeof(double) * g.LD, sizeof(double) * g.NY, g.NX,
-                               cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    SEM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ensure_stage(c)) return -1;
+    if (aux_unpad(g, vec, c->dStage, st)) return -1;
+    SEM_CUDA(cudaMemcpyAsync(host, c->dStage, sizeof(double) * (size_t)g.NX * g.NY, cudaMemcpyDeviceToHost, st));
+    SEM_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
