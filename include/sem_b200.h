@@ -88,6 +88,12 @@ long long sem_ctx_vec_len(const sem_ctx *ctx); /* doubles per vec = NX_local*LD 
 /* launch tuning: elements per strip in y and per marching chunk in x (0 = automatic) */
 int sem_ctx_set_tiling(sem_ctx *ctx, int Ty, int Mx);
 
+/* ---- multi-GPU: one process per GPU, element columns [m_begin, m_end) per rank (sem_mesh_desc).  Rank 0 creates a
+ * 128-byte NCCL unique id, the caller distributes it (torch.distributed), every rank attaches.  Afterwards every operator
+ * apply ends with the NCCL exchange of the interface node line(s) and every dot product is all-reduced. */
+int sem_nccl_unique_id(unsigned char *out128);
+int sem_ctx_attach_comm(sem_ctx *ctx, const unsigned char *id128, int rank, int world);
+
 /* ---- host <-> device packing of the reference's dense vectors (the numpy <-> device boundary) ----------------- */
 int sem_h2d(sem_ctx *ctx, const double *host_local, double *vec, void *stream);
 int sem_d2h(sem_ctx *ctx, const double *vec, double *host_local, void *stream);
@@ -128,6 +134,7 @@ int sem_ns_solve(sem_ctx *ctx, const sem_ns_state *st, const double *rhs3, doubl
                  double *work, long long work_len, void *stream);
 
 /* ---- reductions used by the Python layer (deterministic two-stage sums) ---------------------------------------- */
+/* n = (number of fields) * sem_ctx_vec_len(); interface lines are counted once and the sum is global over ranks */
 int sem_dot(sem_ctx *ctx, const double *x, const double *y, long long n, double *host_out, void *stream);
 /* y = a*x + b*y over n doubles (b == 0: y = a*x); the Newton update u += du of NS:265-267 / T + dT of CD:170 */
 int sem_axpby(sem_ctx *ctx, double a, const double *x, double b, double *y, long long n, void *stream);

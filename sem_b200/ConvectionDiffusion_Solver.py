@@ -17,11 +17,13 @@ from .device import SemDevice
 class ConvectionDiffusionSolver:
     def __init__(self, L_x: float, L_y: float, Pe: float, P: int, N_ex: int, N_ey: int,
                  T_W: float = None, T_E: float = None, T_S: float = None, T_N: float = None,
-                 mtol=1e-7, iprint: list = [], device: int = None, restart: int = None, precond: str = 'jacobi'):
+                 mtol=1e-7, iprint: list = [], device: int = None, restart: int = None, precond: str = 'jacobi',
+                 partition=None):
         """
         Steady convection-diffusion ``Pe [u, v].grad T = lap T`` on [0,L_x]x[0,L_y] with Dirichlet (value) or
         homogeneous Neumann (None) sides -- arguments as CD:10-35.  Extra, optional: ``device`` (CUDA ordinal),
-        ``restart`` (Krylov basis size), ``precond`` ('jacobi' | 'none').
+        ``restart`` (Krylov basis size), ``precond`` ('jacobi' | 'none'), ``partition`` = (rank, world): this process
+        owns one strip of element columns and takes/returns the matching slab of every global vector.
         """
         self._iprint = iprint
         self._Pe = Pe
@@ -33,7 +35,7 @@ class ConvectionDiffusionSolver:
         self._points = None
         self._points_e = None
 
-        self._dev = SemDevice(P, N_ex, N_ey, self._dx, self._dy, device=device)
+        self._dev = SemDevice(P, N_ex, N_ey, self._dx, self._dy, device=device, partition=partition)
         self._lib = self._dev.lib
         self._bc = L.sem_cd_bc()
         for k, val in enumerate((T_W, T_E, T_S, T_N)):          # W, E, S, N: later sides win (CD:62-71)
@@ -56,7 +58,9 @@ class ConvectionDiffusionSolver:
     @property
     def points(self):
         if self._points is None:
-            self._points = SEM.global_nodes(self._P, self._N_ex, self._N_ey, self._dx, self._dy)
+            pts = SEM.global_nodes(self._P, self._N_ex, self._N_ey, self._dx, self._dy)
+            part = self._dev.part
+            self._points = pts if part is None else np.stack([part.local_slice(pts[0]), part.local_slice(pts[1])])
         return self._points
 
     @property

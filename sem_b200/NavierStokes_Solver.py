@@ -24,7 +24,7 @@ class NavierStokesSolver:
     def __init__(self, L_x: float, L_y: float, Re: float, Gr: float, P: int, N_ex: int, N_ey: int,
                  v_W: float = 0, v_E: float = 0, u_S: float = 0, u_N: float = 0,
                  mtol=1e-7, mtol_newton=1e-5, iprint: list = ['NEWTON_suc', 'NEWTON_iter'],
-                 device: int = None, restart: int = None, max_newton: int = 50):
+                 device: int = None, restart: int = None, max_newton: int = 50, partition=None):
         """Arguments as NS:11-41.  Extra, optional: ``device``, ``restart`` (Krylov basis size), ``max_newton``."""
         self._iprint = iprint
         self._Re = Re
@@ -43,7 +43,7 @@ class NavierStokesSolver:
         self._k = 0
         self._max_newton = max_newton
 
-        self._dev = SemDevice(P, N_ex, N_ey, self._dx, self._dy, device=device)
+        self._dev = SemDevice(P, N_ex, N_ey, self._dx, self._dy, device=device, partition=partition)
         self._lib = self._dev.lib
         self._bc = L.sem_ns_bc(float(v_W), float(v_E), float(u_S), float(u_N))
         d = self._dev
@@ -63,7 +63,9 @@ class NavierStokesSolver:
     @property
     def points(self):
         if self._points is None:
-            self._points = SEM.global_nodes(self._P, self._N_ex, self._N_ey, self._dx, self._dy)
+            pts = SEM.global_nodes(self._P, self._N_ex, self._N_ey, self._dx, self._dy)
+            part = self._dev.part
+            self._points = pts if part is None else np.stack([part.local_slice(pts[0]), part.local_slice(pts[1])])
         return self._points
 
     @property
@@ -191,9 +193,9 @@ class NavierStokesSolver:
     def _get_solution(self, T, u0=None, v0=None, p0=None):
         """Newton iteration, device resident; updates u0, v0, p0 in place like NS:248-267 and returns them."""
         d = self._dev
-        u = u0 if u0 is not None else np.zeros(self.N)
-        v = v0 if v0 is not None else np.zeros(self.N)
-        p = p0 if p0 is not None else np.zeros(self.N)
+        u = u0 if u0 is not None else np.zeros(self._dev.N_local)
+        v = v0 if v0 is not None else np.zeros(self._dev.N_local)
+        p = p0 if p0 is not None else np.zeros(self._dev.N_local)
         state = d.zeros(3)
         for k, a in enumerate((u, v, p)):
             d.to_device(a, state[k])

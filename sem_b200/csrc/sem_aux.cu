@@ -56,9 +56,11 @@ __global__ void k_kdiag(const MeshDev g, const TabDev t, double* __restrict__ d)
     const int ix = (int)(idx / g.LD), iy = (int)(idx % g.LD);
     double v = 0.0;
     if (iy < g.NY) {
-        const double wxA = 0.5 * g.dx * asm_w(t.w, g.P, ix, g.nex);
+        // diagonal of the GLOBAL assembled K: global line index, so interface lines carry both ranks' elements
+        const int gix = g.gx0 + ix, nexg = (g.NXg - 1) / g.P;
+        const double wxA = 0.5 * g.dx * asm_w(t.w, g.P, gix, nexg);
         const double wyA = 0.5 * g.dy * asm_w(t.w, g.P, iy, g.ney);
-        v = wyA * (2.0 / g.dx) * asm_kdiag(t.Ks, g.P, ix, g.nex) + wxA * (2.0 / g.dy) * asm_kdiag(t.Ks, g.P, iy, g.ney);
+        v = wyA * (2.0 / g.dx) * asm_kdiag(t.Ks, g.P, gix, nexg) + wxA * (2.0 / g.dy) * asm_kdiag(t.Ks, g.P, iy, g.ney);
     }
     d[idx] = v;
 }
@@ -420,8 +422,8 @@ __global__ void k_ns_schur_mass(const MeshDev g, const TabDev t, const double* _
         const int gix = g.gx0 + ix;
         const bool bnd = (gix == 0) || (gix == g.NXg - 1) || (iy == 0) || (iy == g.NY - 1);
         const bool pin = (gix == pin_gx) && (iy == pin_iy);
-        const double m = (0.5 * g.dx * asm_w(t.w, g.P, ix, g.nex)) * (0.5 * g.dy * asm_w(t.w, g.P, iy, g.ney));
-        v = rc[idx];
+        const double m = (0.5 * g.dx * asm_w(t.w, g.P, gix, (g.NXg - 1) / g.P)) * (0.5 * g.dy * asm_w(t.w, g.P, iy, g.ney));
+        v = rc[idx];   // m: GLOBAL assembled mass
         if (!bnd && !pin) v -= div[idx];
         if (!pin) v /= m;
     }

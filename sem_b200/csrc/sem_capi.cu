@@ -1,6 +1,7 @@
 // C ABI of sem_b200 (see include/sem_b200.h): context, host<->device packing, fused operators, Krylov solvers.
 #include "../../include/sem_b200.h"
 #include "sem_aux.cuh"
+#include "sem_comm.cuh"
 #include "sem_dispatch.h"
 #include "sem_march.cuh"
 
@@ -40,6 +41,8 @@ struct sem_ctx {
     double* d_small;         // device staging for reduction results
     double* h_small;         // pinned mirror
     int small_len;
+    Comm comm;               // NCCL communicator of the element-column partition (has_comm)
+    int has_comm;
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
 };
 
@@ -114,6 +117,7 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     cudaFree(c->dD); cudaFree(c->dKs); cudaFree(c->dw);
     if (c->dKdiag) cudaFree(c->dKdiag);
     if (c->dStage) cudaFree(c->dStage);
+    if (c->has_comm) comm_destroy(c->comm);
     cudaFree(c->rs.partials); cudaFree(c->rs.counter);
     cudaFree(c->d_small); cudaFreeHost(c->h_small);
     delete c;
@@ -127,6 +131,36 @@ extern "C" int sem_ctx_set_tiling(sem_ctx* c, int Ty, int Mx) {
     if (!c) return -2;
     c->Ty_req = Ty;
     c->Mx_req = Mx;
+    return 0;
+}
+
+extern "C" int sem_nccl_unique_id(unsigned char* out128) { return comm_unique_id(out128); }
+
+extern "C" int sem_ctx_attach_comm(sem_ctx* c, const unsigned char* id128, int rank, int world) {
+    SEM_CHECK_CTX(c);
+    if (c->has_comm) { set_error("sem_ctx_attach_comm: communicator already attached"); return -2; }
+    if (comm_init(c->comm, id128, rank, world, c->g.NY)) return -1;
+    c->has_comm = 1;
+    return 0;
+}
+
+// interface exchange of freshly applied operator outputs (no-op on one GPU)
+static int exchange(sem_ctx* c, std::initializer_list<double*> fields, cudaStream_t st) {
+    if (!c->has_comm) return 0;
+    double* f[8];
+    int n = 0;
+    for (double* p : fields)
+        if (p) f[n++] = p;
+    if (n == 0) return 0;
+    return comm_exchange_add(c->comm, c->g, f, n, st);
+}
+
+// k dot products over the owned nodes of this rank, summed over all ranks (deterministic two-stage local sums)
+static int ctx_multi_dot(sem_ctx* c, const double* V, long long n, int k, const double* w, double* h, int nf,
+                         long long vlen, cudaStream_t st) {
+    const long long skip = c->g.has_left ? c->g.LD : 0;   // the interface line is counted by the left rank
+    if (aux_multi_dot(V, n, k, w, h, nf, vlen, skip, c->rs, st)) return -1;
+    if (c->has_comm) return comm_allreduce_sum(c->comm, h, k, st);
     return 0;
 }
 
@@ -206,7 +240,8 @@ extern "C" int sem_apply_stiffness(sem_ctx* c, const double* x, double* y, void*
     MarchArgs A = zero_args();
     A.a = x;
     A.y0 = y;
-    return march(c, MODE_K, A, (cudaStream_t)stream);
+    if (march(c, MODE_K, A, (cudaStream_t)stream)) return -1;
+    return exchange(c, {y}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_apply_gradient(sem_ctx* c, const double* x, double scale, double* gx, double* gy, void* stream) {
@@ -216,22 +251,26 @@ extern "C" int sem_apply_gradient(sem_ctx* c, const double* x, double scale, dou
     A.y0 = gx;
     A.y1 = gy;
     A.cconv = scale;
-    return march(c, MODE_G, A, (cudaStream_t)stream);
+    if (march(c, MODE_G, A, (cudaStream_t)stream)) return -1;
+    return exchange(c, {gx, gy}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_apply_mass(sem_ctx* c, const double* x, double* y, void* stream) {
     SEM_CHECK_CTX(c);
-    return aux_mass_apply(c->g, c->tab(), x, y, (cudaStream_t)stream);
+    if (aux_mass_apply(c->g, c->tab(), x, y, (cudaStream_t)stream)) return -1;
+    return exchange(c, {y}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_mass_diag(sem_ctx* c, double* m, void* stream) {
     SEM_CHECK_CTX(c);
-    return aux_mass_apply(c->g, c->tab(), nullptr, m, (cudaStream_t)stream);
+    if (aux_mass_apply(c->g, c->tab(), nullptr, m, (cudaStream_t)stream)) return -1;
+    return exchange(c, {m}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_gather_scatter(sem_ctx* c, const double* elem, double* y, void* stream) {
     SEM_CHECK_CTX(c);
-    return aux_gather_scatter(c->g, elem, y, (cudaStream_t)stream);
+    if (aux_gather_scatter(c->g, elem, y, (cudaStream_t)stream)) return -1;
+    return exchange(c, {y}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_scatter(sem_ctx* c, const double* x, double* elem, void* stream) {
@@ -245,7 +284,8 @@ extern "C" int sem_cd_residual(sem_ctx* c, const sem_cd_state* s, const double* 
     MarchArgs A = zero_args();
     A.a = T; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = res;
     fill_cd_bc(A.bc, s->bc, 1);
-    return march(c, MODE_CD, A, (cudaStream_t)stream);
+    if (march(c, MODE_CD, A, (cudaStream_t)stream)) return -1;
+    return exchange(c, {res}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_cd_jacobians(sem_ctx* c, double Pe, const double* T, double* gxT, double* gyT, void* stream) {
@@ -260,7 +300,8 @@ extern "C" int sem_cd_jvp(sem_ctx* c, const sem_cd_state* s, const double* dT, c
     A.a = dT; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = dres;
     A.d0 = s->gxT; A.e0 = du; A.d1 = s->gyT; A.e1 = dv;
     fill_cd_bc(A.bc, s->bc, 0);
-    return march(c, MODE_CD, A, (cudaStream_t)stream);
+    if (march(c, MODE_CD, A, (cudaStream_t)stream)) return -1;
+    return exchange(c, {dres}, (cudaStream_t)stream);
 }
 
 // ---- Navier-Stokes ------------------------------------------------------------------------------------------------
@@ -275,7 +316,8 @@ extern "C" int sem_ns_residual(sem_ctx* c, const sem_ns_state* s, const double* 
     int rcode = march(c, MODE_NS, A, (cudaStream_t)stream);
     if (rcode) return rcode;
     // NS:116-119: pin first, then the Neumann rows (they win if the pin sits on the boundary)
-    return aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, (cudaStream_t)stream);
+    if (aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, (cudaStream_t)stream)) return -1;
+    return exchange(c, {ru, rv, rc}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_ns_jacobians(sem_ctx* c, double Re, const double* u, const double* v, double* gxu, double* gyu,
@@ -298,14 +340,17 @@ extern "C" int sem_ns_jvp(sem_ctx* c, const sem_ns_state* s, const double* du, c
     int rcode = march(c, MODE_NS, A, (cudaStream_t)stream);
     if (rcode) return rcode;
     // NS:157-158: Neumann rows first, then the pin (the pin wins)
-    return aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, (cudaStream_t)stream);
+    if (aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, (cudaStream_t)stream)) return -1;
+    return exchange(c, {ou, ov, oc}, (cudaStream_t)stream);
 }
 
 // ---- reductions ------------------------------------------------------------------------------------------------------
 extern "C" int sem_dot(sem_ctx* c, const double* x, const double* y, long long n, double* host_out, void* stream) {
     SEM_CHECK_CTX(c);
     cudaStream_t st = (cudaStream_t)stream;
-    if (aux_multi_dot(x, n, 1, y, c->d_small, 1, n, 0, c->rs, st)) return -1;
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    if (n % vlen != 0) { set_error("sem_dot: n must be a multiple of the field length"); return -2; }
+    if (ctx_multi_dot(c, x, n, 1, y, c->d_small, (int)(n / vlen), vlen, st)) return -1;
     SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double), cudaMemcpyDeviceToHost, st));
     SEM_CUDA(cudaStreamSynchronize(st));
     *host_out = c->h_small[0];
@@ -340,9 +385,8 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gv(m + 1), yv(m);
     kr->iters = 0;
     kr->resnorm = -1.0;
-    const long long skip = 0;
     auto norm2 = [&](const double* v, double* out) -> int {
-        if (aux_multi_dot(v, n, 1, v, c->d_small, L.nf, L.vlen, skip, c->rs, st)) return -1;
+        if (ctx_multi_dot(c, v, n, 1, v, c->d_small, L.nf, L.vlen, st)) return -1;
         SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double), cudaMemcpyDeviceToHost, st));
         SEM_CUDA(cudaStreamSynchronize(st));
         *out = std::sqrt(c->h_small[0]);
@@ -373,11 +417,11 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
             double* h1 = c->d_small;
             double* h2 = c->d_small + (j + 1);
             double* nr = c->d_small + 2 * (j + 1);
-            if (aux_multi_dot(V, n, j + 1, w, h1, L.nf, L.vlen, skip, c->rs, st)) return -1;
+            if (ctx_multi_dot(c, V, n, j + 1, w, h1, L.nf, L.vlen, st)) return -1;
             if (aux_multi_axpy(V, n, j + 1, h1, -1.0, w, st)) return -1;
-            if (aux_multi_dot(V, n, j + 1, w, h2, L.nf, L.vlen, skip, c->rs, st)) return -1;
+            if (ctx_multi_dot(c, V, n, j + 1, w, h2, L.nf, L.vlen, st)) return -1;
             if (aux_multi_axpy(V, n, j + 1, h2, -1.0, w, st)) return -1;
-            if (aux_multi_dot(w, n, 1, w, nr, L.nf, L.vlen, skip, c->rs, st)) return -1;
+            if (ctx_multi_dot(c, w, n, 1, w, nr, L.nf, L.vlen, st)) return -1;
             if (aux_scale_inv_norm(w, nr, V + (long long)(j + 1) * n, n, st)) return -1;
             SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double) * (2 * (j + 1) + 1), cudaMemcpyDeviceToHost, st));
             SEM_CUDA(cudaStreamSynchronize(st));
@@ -492,6 +536,7 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
         MarchArgs A = zero_args();
         A.a = z; A.b = z + vlen; A.y0 = tmp;
         if (march(c, MODE_DIV, A, st)) return -1;
+        if (exchange(c, {tmp}, st)) return -1;
         return aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st);
     };
     GmresLayout L{n, 3, vlen};

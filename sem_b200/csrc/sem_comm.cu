@@ -1,0 +1,149 @@
+#include "sem_comm.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace semb {
+
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) { set_error(std::string("cannot dlopen libnccl: ") + dlerror()); return -1; }
+#define SEM_SYM(field, sym)                                                    \
+    *(void**)(&g_nccl.field) = dlsym(h, sym);                                  \
+    if (!g_nccl.field) { set_error(std::string("libnccl lacks ") + sym); return -1; }
+    SEM_SYM(GetUniqueId, "ncclGetUniqueId")
+    SEM_SYM(CommInitRank, "ncclCommInitRank")
+    SEM_SYM(CommDestroy, "ncclCommDestroy")
+    SEM_SYM(AllReduce, "ncclAllReduce")
+    SEM_SYM(Send, "ncclSend")
+    SEM_SYM(Recv, "ncclRecv")
+    SEM_SYM(GroupStart, "ncclGroupStart")
+    SEM_SYM(GroupEnd, "ncclGroupEnd")
+    SEM_SYM(GetErrorString, "ncclGetErrorString")
+#undef SEM_SYM
+    g_nccl.handle = h;
+    return 0;
+}
+}  // namespace
+
+#define SEM_NCCL(call)                                                                                       \
+    do {                                                                                                     \
+        ncclResult_t _r = (call);                                                                            \
+        if (_r != ncclSuccess) {                                                                             \
+            set_error(std::string(#call) + " failed: " + g_nccl.GetErrorString(_r));                         \
+            return -4;                                                                                       \
+        }                                                                                                    \
+    } while (0)
+
+static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+
+int comm_unique_id(unsigned char out[128]) {
+    if (load_nccl()) return -1;
+    ncclUniqueId id;
+    SEM_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out, &id, 128);
+    return 0;
+}
+
+int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY) {
+    if (load_nccl()) return -1;
+    ncclUniqueId id;
+    memcpy(&id, idb, 128);
+    ncclComm_t comm;
+    SEM_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+    c.nccl = comm;
+    c.rank = rank;
+    c.world = world;
+    c.max_fields = 4;
+    SEM_CUDA(cudaMalloc(&c.recv, sizeof(double) * 2 * c.max_fields * (size_t)NY));
+    return 0;
+}
+
+void comm_destroy(Comm& c) {
+    if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
+    if (c.recv) cudaFree(c.recv);
+    c.nccl = nullptr;
+    c.recv = nullptr;
+}
+
+int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st) {
+    SEM_NCCL(g_nccl.AllReduce(buf, buf, (size_t)k, ncclDouble, ncclSum, (ncclComm_t)c.nccl, st));
+    return 0;
+}
+
+// line[f][iy] = a + b with the LOWER rank's partial sum first (a two-term IEEE sum is order independent, but the order
+// is fixed anyway so the code reads as what it guarantees)
+
+struct LinePtrs {
+    double* line[8];
+    const double* recv[8];
+    int lower_first[8];
+    int n;
+};
+
+__global__ void k_halo_add(const LinePtrs p, int NY) {
+    const int iy = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (iy >= NY || q >= p.n) return;
+    const double mine = p.line[q][iy], other = p.recv[q][iy];
+    p.line[q][iy] = p.lower_first[q] ? (mine + other) : (other + mine);
+}
+
+int comm_exchange_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    if (nf > c.max_fields) { set_error("comm_exchange_add: too many fields"); return -2; }
+    if (!g.has_left && !g.has_right) return 0;
+    ncclComm_t comm = (ncclComm_t)c.nccl;
+    const size_t NY = (size_t)g.NY;
+    const size_t last = (size_t)(g.NX - 1) * g.LD;
+    LinePtrs lp;
+    lp.n = 0;
+    SEM_NCCL(g_nccl.GroupStart());
+    for (int f = 0; f < nf; ++f) {
+        if (g.has_left) {
+            double* rbuf = c.recv + (size_t)(0 * c.max_fields + f) * NY;
+            SEM_NCCL(g_nccl.Send(fields[f], NY, ncclDouble, c.rank - 1, comm, st));
+            SEM_NCCL(g_nccl.Recv(rbuf, NY, ncclDouble, c.rank - 1, comm, st));
+            lp.line[lp.n] = fields[f];
+            lp.recv[lp.n] = rbuf;
+            lp.lower_first[lp.n] = 0;   // the neighbour is the lower rank: its partial goes first
+            lp.n++;
+        }
+        if (g.has_right) {
+            double* rbuf = c.recv + (size_t)(1 * c.max_fields + f) * NY;
+            SEM_NCCL(g_nccl.Send(fields[f] + last, NY, ncclDouble, c.rank + 1, comm, st));
+            SEM_NCCL(g_nccl.Recv(rbuf, NY, ncclDouble, c.rank + 1, comm, st));
+            lp.line[lp.n] = fields[f] + last;
+            lp.recv[lp.n] = rbuf;
+            lp.lower_first[lp.n] = 1;
+            lp.n++;
+        }
+    }
+    SEM_NCCL(g_nccl.GroupEnd());
+    dim3 grid((unsigned)((g.NY + 255) / 256), (unsigned)lp.n);
+    k_halo_add<<<grid, 256, 0, st>>>(lp, g.NY);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace semb

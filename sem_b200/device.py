@@ -24,13 +24,18 @@ def default_device():
 
 
 class SemDevice:
-    def __init__(self, P, N_ex, N_ey, dx, dy, device=None, m_begin=0, m_end=None):
+    def __init__(self, P, N_ex, N_ey, dx, dy, device=None, m_begin=0, m_end=None, partition=None):
         if not torch.cuda.is_available():
             raise L.SemError("sem_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = L.load()
         self.P, self.N_ex, self.N_ey = int(P), int(N_ex), int(N_ey)
         self.dx, self.dy = float(dx), float(dy)
         self.device = default_device() if device is None else int(device)
+        self.part = None
+        if partition is not None:                       # (rank, world): strip of element columns of this rank
+            from .partition import Partition
+            self.part = Partition(self.N_ex, self.N_ey, self.P, int(partition[0]), int(partition[1]))
+            m_begin, m_end = self.part.m_begin, self.part.m_end
         self.m_begin = int(m_begin)
         self.m_end = self.N_ex if m_end is None else int(m_end)
         self.tdev = torch.device("cuda", self.device)
@@ -50,6 +55,23 @@ class SemDevice:
         self.vec_len = self.lib.sem_ctx_vec_len(ctx)
         self.N_local = self.NX * self.NY
         self._pinned = {}
+        if self.part is not None and self.part.world > 1:
+            self._attach_comm()
+
+    def _attach_comm(self):
+        """Create the NCCL communicator of the partition: rank 0 draws the unique id, torch.distributed spreads it."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise L.SemError("partition=(rank, world) needs torch.distributed to be initialised (torchrun)")
+        idbuf = (C.c_ubyte * 128)()
+        if self.part.rank == 0:
+            L.check(self.lib.sem_nccl_unique_id(idbuf), "sem_nccl_unique_id")
+        t = torch.tensor(list(idbuf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.to(self.tdev)
+        dist.broadcast(t, src=0)
+        idbuf = (C.c_ubyte * 128)(*t.cpu().tolist())
+        L.check(self.lib.sem_ctx_attach_comm(self.ctx, idbuf, self.part.rank, self.part.world), "sem_ctx_attach_comm")
 
     def __del__(self):
         try:

@@ -1,0 +1,93 @@
+"""Worker of tests/test_multi_gpu.py (launched with torch.distributed.run, one rank per GPU): the partitioned NCCL
+path against the single-GPU path and the oracle, on identical inputs."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+import sem_b200  # noqa: E402
+from sem_b200.partition import Partition  # noqa: E402
+from oracle import sem_oracle as so  # noqa: E402  (checker)
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fails = []
+
+    def check(name, val, tol):
+        if not (val < tol):
+            fails.append(f"rank {rank}: {name} = {val:.3e} (tol {tol:.0e})")
+
+    # ---- CD: applies, Jacobian, solve --------------------------------------------------------------------------------
+    P, nx, ny = 4, 8, 6
+    kw = dict(L_x=1.5, L_y=1.0, Pe=25.0, P=P, N_ex=nx, N_ey=ny, T_W=0.5, T_E=-0.5, T_S=0.1)
+    part = Partition(nx, ny, P, rank, world)
+    cd = sem_b200.ConvectionDiffusionSolver(mtol=1e-12, device=local, partition=(rank, world), **kw)
+    cd_o = so.CDOracle(mtol=1e-12, **kw)
+    rng = np.random.default_rng(3)
+    T, u, v, dT, du, dv = (rng.standard_normal(cd_o.N) for _ in range(6))
+    sl = part.local_slice
+    check("cd residual", relerr(cd._get_residuals(sl(T), sl(u), sl(v)), sl(cd_o._get_residuals(T, u, v))), 1e-12)
+    cd._calc_jacobians(sl(T))
+    cd_o._calc_jacobians(T)
+    check("cd jvp", relerr(cd._get_dresiduals(sl(dT), sl(du), sl(dv)), sl(cd_o._get_dresiduals(dT, du, dv))), 1e-12)
+    uu = cd_o._get_vector(lambda x, y: y - 0.5)
+    vv = cd_o._get_vector(lambda x, y: 0.75 - x)
+    check("cd solve", relerr(cd._get_solution(sl(uu), sl(vv)), sl(cd_o._get_solution(uu, vv))), 1e-8)
+    check("cd points", float(np.abs(cd.points - np.stack([sl(cd_o.points[0]), sl(cd_o.points[1])])).max()), 1e-15)
+
+    # ---- NS: applies and a Newton solve --------------------------------------------------------------------------------
+    nkw = dict(L_x=1.0, L_y=1.0, Re=50.0, Gr=200.0, P=3, N_ex=4, N_ey=4, u_N=1.0)
+    part = Partition(4, 4, 3, rank, world)
+    sl = part.local_slice
+    ns = sem_b200.NavierStokesSolver(mtol=1e-13, mtol_newton=1e-13, iprint=[], device=local, partition=(rank, world), **nkw)
+    ns_o = so.NSOracle(mtol=1e-13, mtol_newton=1e-13, **nkw)
+    a, b, c, d, e = (rng.standard_normal(ns_o.N) for _ in range(5))
+    for x, y in zip(ns._get_residuals(sl(a), sl(b), sl(c), sl(d)), ns_o._get_residuals(a, b, c, d)):
+        check("ns residual", relerr(x, sl(y)), 1e-12)
+    ns._calc_jacobians(sl(a), sl(b))
+    ns_o._calc_jacobians(a, b)
+    for x, y in zip(ns._get_dresiduals(sl(c), sl(d), sl(e), sl(a)), ns_o._get_dresiduals(c, d, e, a)):
+        check("ns jvp", relerr(x, sl(y)), 1e-12)
+    Tin = ns_o._get_vector(lambda x, y: 0.5 - x)
+    us, vs, ps = ns._get_solution(sl(Tin))
+    uo, vo, po = ns_o._get_solution(Tin)
+    check("ns solve u", relerr(us, sl(uo)), 1e-8)
+    check("ns solve v", relerr(vs, sl(vo)), 1e-8)
+    check("ns solve p", relerr(ps, sl(po)), 1e-8)
+    if ns._k != ns_o._k:
+        fails.append(f"rank {rank}: Newton its {ns._k} vs {ns_o._k}")
+
+    # ---- larger stiffness apply: partitioned result == single-GPU result, bitwise away from / to rounding at the interface
+    P, ne = 8, 16 * world
+    dall = sem_b200.SemDevice(P, ne, ne, 1.0 / ne, 1.0 / ne, device=local)
+    dpar = sem_b200.SemDevice(P, ne, ne, 1.0 / ne, 1.0 / ne, device=local, partition=(rank, world))
+    xg = np.random.default_rng(11).standard_normal(dall.N_local)
+    yg = dall.to_host(dall.apply_stiffness(dall.to_device(xg), dall.zeros()))
+    yl = dpar.to_host(dpar.apply_stiffness(dpar.to_device(dpar.part.local_slice(xg)), dpar.zeros()))
+    check("partitioned K apply", relerr(yl, dpar.part.local_slice(yg)), 1e-13)
+    xl = dpar.to_device(dpar.part.local_slice(xg))
+    check("global dot", abs(dpar.dot(xl, xl) - float(xg @ xg)) / float(xg @ xg), 1e-13)
+
+    allf = [None] * world
+    dist.all_gather_object(allf, fails)
+    dist.destroy_process_group()
+    flat = [f for fl in allf for f in fl]
+    if rank == 0:
+        print("MGPU_OK" if not flat else "MGPU_FAIL\n" + "\n".join(flat))
+    sys.exit(1 if flat else 0)
+
+
+if __name__ == "__main__":
+    main()
