@@ -183,17 +183,17 @@ def run_ours(args):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
-    # a short run leaves the sampler without a sample under load: keep the load up until it has a few
-    if sampler:
-        t_end = time.time() + 1.5
-        while len(sampler.rows) < 5 and time.time() < t_end:
-            step()
-        torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
     if world > 1:
         t = torch.tensor([ms], device=d.tdev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # a short run leaves the clock sampler without a sample under load: keep the same load up for ~1.5 s more.
+    # The count is derived from the all-reduced time so that EVERY rank issues the same number of (collective) steps.
+    extra_steps = int(min(5000, max(0, 1500.0 / max(ms / steps, 1e-3))))
+    for _ in range(extra_steps):
+        step()
+    sync_all()
+    clocks = sampler.stop() if sampler else None
     ms_per_step = ms / steps
     value = n_global / (ms_per_step * 1e-3) / 1e9
 

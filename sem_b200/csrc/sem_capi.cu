@@ -4,6 +4,8 @@
 #include "sem_comm.cuh"
 #include "sem_dispatch.h"
 #include "sem_march.cuh"
+#include "sem_march2.cuh"
+#include <cstdlib>
 
 #include <cmath>
 #include <cstring>
@@ -22,11 +24,13 @@ typedef int (*march_fn)(int, const MeshDev&, const MarchArgs&, const MarchGeom&,
 typedef size_t (*smem_fn)(int, int);
 typedef int (*upload_fn)(const double*, const double*, const double*);
 
-#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P},
+#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P, march2_launch_p##P, march2_smem_p##P},
 static const struct {
     march_fn launch;
     smem_fn smem;
     upload_fn upload;
+    march_fn launch2;
+    smem_fn smem2;
 } g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
 
 struct sem_ctx {
@@ -193,8 +197,21 @@ extern "C" int sem_d2h(sem_ctx* c, const double* vec, double* host, void* stream
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// SEM_B200_MARCH=1 forces the v1 kernel everywhere (A/B comparisons); default: v2 where it exists.
+static bool want_v2() {
+    static const int v = [] { const char* e = std::getenv("SEM_B200_MARCH"); return (e && e[0] == '1') ? 0 : 1; }();
+    return v != 0;
+}
+
 static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
     A.zero = 0;
+    const auto& ord = g_orders[c->g.P - 1];
+    if (want_v2() && ord.smem2(mode, 32) != 0) {
+        MarchGeom q = march2_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
+        while (ord.smem2(mode, q.pitch) > (size_t)c->smem_optin && q.Ty > 1)
+            q = march2_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count);
+        return ord.launch2(mode, c->g, A, q, st);
+    }
     MarchGeom q = march_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
     // shrink the strip until the tile fits the opt-in shared memory of the device
     while (g_orders[c->g.P - 1].smem(mode, q.pitch) > (size_t)c->smem_optin && q.Ty > 1) {

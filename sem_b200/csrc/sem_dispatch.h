@@ -10,6 +10,8 @@ struct MarchGeom;
 #define SEM_DECL_P(P)                                                                                         \
     int march_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
     size_t march_smem_p##P(int mode, int pitch);                                                               \
+    int march2_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
+    size_t march2_smem_p##P(int mode, int pitch);                                                              \
     int upload_tab_p##P(const double* D, const double* Ks, const double* w);
 SEM_FOR_EACH_P(SEM_DECL_P)
 #undef SEM_DECL_P

@@ -144,20 +144,21 @@ struct March {
         }
     }
 
-    // ---- finish one node: add x- and y-parts, pointwise terms, boundary rows; store ----------------------------------
-    static __device__ __forceinline__ void finish(const MeshDev& g, const MarchArgs& A, int ix, int iy,
-                                                  const double (&xp)[NOUT], const double (&yp)[NACC],
-                                                  const double (&node)[NF], double wxA_line, double wyA) {
+    // ---- finish one node: add x- and y-parts, pointwise terms, boundary rows -> out[] (the caller stores) ---------------
+    static __device__ __forceinline__ void finish_vals(const MeshDev& g, const MarchArgs& A, int ix, int iy,
+                                                       const double (&xp)[NOUT], const double (&yp)[NACC],
+                                                       const double (&node)[NF], double wxA_line, double wyA,
+                                                       double (&out)[NOUT]) {
         const int off = ix * g.LD + iy;
         const int gix = g.gx0 + ix;
         // interface lines are duplicated on two ranks: the element sums of both ranks are added by the halo exchange,
         // pointwise terms and boundary rows are contributed by the owner only (the rank for which it is NOT the last line)
         const bool owner = !(g.has_right && ix == g.NX - 1);
         if constexpr (MODE == MODE_K || MODE == MODE_DIV) {
-            A.y0[off] = xp[0] + yp[0];
+            out[0] = xp[0] + yp[0];
         } else if constexpr (MODE == MODE_G) {
-            if (A.y0) A.y0[off] = xp[0];
-            if (A.y1) A.y1[off] = yp[0];
+            out[0] = xp[0];
+            out[1] = yp[0];
         } else if constexpr (MODE == MODE_CD) {
             double r0 = xp[0] + yp[0];
             if (owner) {
@@ -166,7 +167,7 @@ struct March {
             }
             const int side = bc_side(A.bc, gix, iy, g.NXg, g.NY);
             if (side >= 0) r0 = owner ? (node[0] - (A.bc.residual ? A.bc.val0[side] : 0.0)) : 0.0;
-            A.y0[off] = r0;
+            out[0] = r0;
         } else {
             double r0 = xp[0] + yp[0];
             double r1 = xp[1] + yp[1];
@@ -182,10 +183,22 @@ struct March {
                 r1 = owner ? (node[1] - (A.bc.residual ? A.bc.val1[side] : 0.0)) : 0.0;
             }
             if (gix == A.bc.pin_gx && iy == A.bc.pin_iy) r2 = owner ? node[2] : 0.0;
-            A.y0[off] = r0;
-            A.y1[off] = r1;
-            A.y2[off] = r2;
+            out[0] = r0;
+            out[1] = r1;
+            out[2] = r2;
         }
+    }
+
+    static __device__ __forceinline__ void finish(const MeshDev& g, const MarchArgs& A, int ix, int iy,
+                                                  const double (&xp)[NOUT], const double (&yp)[NACC],
+                                                  const double (&node)[NF], double wxA_line, double wyA) {
+        double out[NOUT];
+        finish_vals(g, A, ix, iy, xp, yp, node, wxA_line, wyA, out);
+        const int off = ix * g.LD + iy;
+        double* const y[3] = {A.y0, A.y1, A.y2};
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o)
+            if (MODE != MODE_G || y[o]) y[o][off] = out[o];
     }
 
     template <int I>
