@@ -144,6 +144,54 @@ struct March {
         }
     }
 
+    // ---- the same row formulas with the contraction results passed in (used by the v2 kernel, which computes the
+    //      contractions with folded even/odd tables): sK[f] = (Ks a_f)_row, sD[f] = (D a_f)_row -------------------------
+    static constexpr bool x_needs_K(int f) { return (MODE == MODE_K || MODE == MODE_CD) ? f == 0 : (MODE == MODE_NS ? f < 2 : false); }
+    static constexpr bool x_needs_D(int f) { return (MODE == MODE_NS) ? true : (MODE == MODE_K ? false : f == 0); }
+    static constexpr bool y_needs_K(int f) { return x_needs_K(f); }
+    static constexpr bool y_needs_D(int f) { return (MODE == MODE_NS) ? true : (MODE == MODE_K ? false : (MODE == MODE_DIV ? f == 1 : f == 0)); }
+
+    template <int I>
+    static __device__ __forceinline__ void xcombine(const double (&sK)[NF], const double (&sD)[NF], double Uc,
+                                                    double cKx, double wyA, double cc, double (&x)[NOUT]) {
+        const double gw = c_tab<P>.w[I] * wyA;
+        if constexpr (MODE == MODE_K) {
+            x[0] = cKx * sK[0];
+        } else if constexpr (MODE == MODE_G) {
+            x[0] = cc * gw * sD[0];
+            x[1] = 0.0;
+        } else if constexpr (MODE == MODE_CD) {
+            x[0] = fma(cc * Uc * gw, sD[0], cKx * sK[0]);
+        } else if constexpr (MODE == MODE_DIV) {
+            x[0] = gw * sD[0];
+        } else {
+            const double cu = cc * Uc * gw;
+            x[0] = fma(gw, sD[2], fma(cu, sD[0], cKx * sK[0]));
+            x[1] = fma(cu, sD[1], cKx * sK[1]);
+            x[2] = gw * sD[0];
+        }
+    }
+
+    template <int J>
+    static __device__ __forceinline__ void ycombine(const double (&sK)[NF], const double (&sD)[NF], double Vc,
+                                                    double wxK, double wxA, double cc, double (&y)[NACC]) {
+        const double gw = wxA * c_tab<P>.w[J];
+        if constexpr (MODE == MODE_K) {
+            y[0] = wxK * sK[0];
+        } else if constexpr (MODE == MODE_G) {
+            y[0] = cc * gw * sD[0];
+        } else if constexpr (MODE == MODE_CD) {
+            y[0] = fma(cc * Vc * gw, sD[0], wxK * sK[0]);
+        } else if constexpr (MODE == MODE_DIV) {
+            y[0] = gw * sD[1];
+        } else {
+            const double cv = cc * Vc * gw;
+            y[0] = fma(cv, sD[0], wxK * sK[0]);
+            y[1] = fma(gw, sD[2], fma(cv, sD[1], wxK * sK[1]));
+            y[2] = gw * sD[1];
+        }
+    }
+
     // ---- finish one node: add x- and y-parts, pointwise terms, boundary rows -> out[] (the caller stores) ---------------
     static __device__ __forceinline__ void finish_vals(const MeshDev& g, const MarchArgs& A, int ix, int iy,
                                                        const double (&xp)[NOUT], const double (&yp)[NACC],
