@@ -5,6 +5,7 @@
 #include "sem_dispatch.h"
 #include "sem_march.cuh"
 #include "sem_march2.cuh"
+#include "sem_march3.cuh"
 #include <cstdlib>
 
 #include <cmath>
@@ -24,18 +25,21 @@ typedef int (*march_fn)(int, const MeshDev&, const MarchArgs&, const MarchGeom&,
 typedef size_t (*smem_fn)(int, int);
 typedef int (*upload_fn)(const double*, const double*, const double*);
 
-#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P, march2_launch_p##P, march2_smem_p##P},
+#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P, march2_launch_p##P, march2_smem_p##P, march3_launch_p##P, upload_tab3_p##P, march3_smem_p##P},
 static const struct {
     march_fn launch;
     smem_fn smem;
     upload_fn upload;
     march_fn launch2;
     smem_fn smem2;
+    march_fn launch3;
+    upload_fn upload3;
+    size_t (*smem3)(int);
 } g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
 
 struct sem_ctx {
     MeshDev g;
-    int device, sm_count, smem_optin;
+    int device, sm_count, smem_optin, smem_sm;
     int Ty_req, Mx_req;
     int pin_gx, pin_iy;
     double *dD, *dKs, *dw;   // plain device tables
@@ -77,6 +81,7 @@ extern "C" int sem_ctx_create(sem_ctx** out, const sem_mesh_desc* d) {
     c->device = d->device;
     SEM_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, d->device));
     SEM_CUDA(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d->device));
+    SEM_CUDA(cudaDeviceGetAttribute(&c->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, d->device));
     MeshDev& g = c->g;
     g.P = d->P;
     g.nex = d->m_end - d->m_begin;
@@ -103,6 +108,7 @@ extern "C" int sem_ctx_create(sem_ctx** out, const sem_mesh_desc* d) {
     SEM_CUDA(cudaMemcpy(c->dKs, d->Ks, sizeof(double) * n * n, cudaMemcpyHostToDevice));
     SEM_CUDA(cudaMemcpy(c->dw, d->w, sizeof(double) * n, cudaMemcpyHostToDevice));
     if (g_orders[g.P - 1].upload(d->D, d->Ks, d->w)) { delete c; return -1; }
+    if (g_orders[g.P - 1].upload3(d->D, d->Ks, d->w)) { delete c; return -1; }
     c->rs.max_blocks = 2 * c->sm_count;
     c->rs.max_k = SEM_MAX_RESTART + 8;
     SEM_CUDA(cudaMalloc(&c->rs.partials, sizeof(double) * (size_t)c->rs.max_blocks * c->rs.max_k));
@@ -197,16 +203,25 @@ extern "C" int sem_d2h(sem_ctx* c, const double* vec, double* host, void* stream
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// SEM_B200_MARCH=1 forces the v1 kernel everywhere (A/B comparisons); default: v2 where it exists.
-static bool want_v2() {
-    static const int v = [] { const char* e = std::getenv("SEM_B200_MARCH"); return (e && e[0] == '1') ? 0 : 1; }();
-    return v != 0;
+// Kernel generation: v3 (TMA-staged, folded tables) for even orders; v1 for odd orders.  SEM_B200_MARCH=1 / 2 force the
+// older generations (A/B comparisons only).
+static int march_generation() {
+    static const int v = [] {
+        const char* e = std::getenv("SEM_B200_MARCH");
+        return (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+    }();
+    return v;
 }
 
 static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
     A.zero = 0;
     const auto& ord = g_orders[c->g.P - 1];
-    if (want_v2() && ord.smem2(mode, 32) != 0) {
+    const int gen = march_generation();
+    if (gen == 3 && c->g.P % 2 == 0) {
+        const MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm);
+        return ord.launch3(mode, c->g, A, q, st);
+    }
+    if (gen == 2 && ord.smem2(mode, 32) != 0) {
         MarchGeom q = march2_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
         while (ord.smem2(mode, q.pitch) > (size_t)c->smem_optin && q.Ty > 1)
             q = march2_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count);

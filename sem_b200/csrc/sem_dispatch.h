@@ -12,6 +12,9 @@ struct MarchGeom;
     size_t march_smem_p##P(int mode, int pitch);                                                               \
     int march2_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
     size_t march2_smem_p##P(int mode, int pitch);                                                              \
+    int march3_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
+    size_t march3_smem_p##P(int mode);                                                                         \
+    int upload_tab3_p##P(const double* D, const double* Ks, const double* w);                                  \
     int upload_tab_p##P(const double* D, const double* Ks, const double* w);
 SEM_FOR_EACH_P(SEM_DECL_P)
 #undef SEM_DECL_P

@@ -146,10 +146,10 @@ struct March {
 
     // ---- the same row formulas with the contraction results passed in (used by the v2 kernel, which computes the
     //      contractions with folded even/odd tables): sK[f] = (Ks a_f)_row, sD[f] = (D a_f)_row -------------------------
-    static constexpr bool x_needs_K(int f) { return (MODE == MODE_K || MODE == MODE_CD) ? f == 0 : (MODE == MODE_NS ? f < 2 : false); }
-    static constexpr bool x_needs_D(int f) { return (MODE == MODE_NS) ? true : (MODE == MODE_K ? false : f == 0); }
-    static constexpr bool y_needs_K(int f) { return x_needs_K(f); }
-    static constexpr bool y_needs_D(int f) { return (MODE == MODE_NS) ? true : (MODE == MODE_K ? false : (MODE == MODE_DIV ? f == 1 : f == 0)); }
+    static __host__ __device__ constexpr bool x_needs_K(int f) { return (MODE == MODE_K || MODE == MODE_CD) ? f == 0 : (MODE == MODE_NS ? f < 2 : false); }
+    static __host__ __device__ constexpr bool x_needs_D(int f) { return (MODE == MODE_NS) ? true : (MODE == MODE_K ? false : f == 0); }
+    static __host__ __device__ constexpr bool y_needs_K(int f) { return x_needs_K(f); }
+    static __host__ __device__ constexpr bool y_needs_D(int f) { return (MODE == MODE_NS) ? true : (MODE == MODE_K ? false : (MODE == MODE_DIV ? f == 1 : f == 0)); }
 
     template <int I>
     static __device__ __forceinline__ void xcombine(const double (&sK)[NF], const double (&sD)[NF], double Uc,
@@ -193,6 +193,10 @@ struct March {
     }
 
     // ---- finish one node: add x- and y-parts, pointwise terms, boundary rows -> out[] (the caller stores) ---------------
+    // FAST: the caller knows that the node carries no boundary row, is not the pressure pin and does not lie on an
+    // interface line owned by the neighbour rank -- only the element sums and the pointwise terms remain.
+    // PW = false: the pointwise terms are known to be absent (their pointers are null).
+    template <bool FAST = false, bool PW = true>
     static __device__ __forceinline__ void finish_vals(const MeshDev& g, const MarchArgs& A, int ix, int iy,
                                                        const double (&xp)[NOUT], const double (&yp)[NACC],
                                                        const double (&node)[NF], double wxA_line, double wyA,
@@ -201,7 +205,7 @@ struct March {
         const int gix = g.gx0 + ix;
         // interface lines are duplicated on two ranks: the element sums of both ranks are added by the halo exchange,
         // pointwise terms and boundary rows are contributed by the owner only (the rank for which it is NOT the last line)
-        const bool owner = !(g.has_right && ix == g.NX - 1);
+        const bool owner = FAST || !(g.has_right && ix == g.NX - 1);
         if constexpr (MODE == MODE_K || MODE == MODE_DIV) {
             out[0] = xp[0] + yp[0];
         } else if constexpr (MODE == MODE_G) {
@@ -209,28 +213,32 @@ struct March {
             out[1] = yp[0];
         } else if constexpr (MODE == MODE_CD) {
             double r0 = xp[0] + yp[0];
-            if (owner) {
+            if (PW && owner) {
                 if (A.e0) r0 = fma(A.d0[off], A.e0[off], r0);
                 if (A.e1) r0 = fma(A.d1[off], A.e1[off], r0);
             }
-            const int side = bc_side(A.bc, gix, iy, g.NXg, g.NY);
-            if (side >= 0) r0 = owner ? (node[0] - (A.bc.residual ? A.bc.val0[side] : 0.0)) : 0.0;
+            if constexpr (!FAST) {
+                const int side = bc_side(A.bc, gix, iy, g.NXg, g.NY);
+                if (side >= 0) r0 = owner ? (node[0] - (A.bc.residual ? A.bc.val0[side] : 0.0)) : 0.0;
+            }
             out[0] = r0;
         } else {
             double r0 = xp[0] + yp[0];
             double r1 = xp[1] + yp[1];
             double r2 = xp[2] + yp[2];
-            if (A.d0 && owner) {
+            if (PW && A.d0 && owner) {
                 r0 = fma(A.d0[off], node[0], fma(A.d1[off], node[1], r0));
                 r1 = fma(A.d2[off], node[0], fma(A.d3[off], node[1], r1));
             }
-            if (A.e0) r1 = fma(A.cbuoy * (wxA_line * wyA), A.e0[off], r1);  // -(Gr/Re) M T, M is an element sum
-            const int side = bc_side(A.bc, gix, iy, g.NXg, g.NY);
-            if (side >= 0) {
-                r0 = owner ? (node[0] - (A.bc.residual ? A.bc.val0[side] : 0.0)) : 0.0;
-                r1 = owner ? (node[1] - (A.bc.residual ? A.bc.val1[side] : 0.0)) : 0.0;
+            if (PW && A.e0) r1 = fma(A.cbuoy * (wxA_line * wyA), A.e0[off], r1);  // -(Gr/Re) M T, M is an element sum
+            if constexpr (!FAST) {
+                const int side = bc_side(A.bc, gix, iy, g.NXg, g.NY);
+                if (side >= 0) {
+                    r0 = owner ? (node[0] - (A.bc.residual ? A.bc.val0[side] : 0.0)) : 0.0;
+                    r1 = owner ? (node[1] - (A.bc.residual ? A.bc.val1[side] : 0.0)) : 0.0;
+                }
+                if (gix == A.bc.pin_gx && iy == A.bc.pin_iy) r2 = owner ? node[2] : 0.0;
             }
-            if (gix == A.bc.pin_gx && iy == A.bc.pin_iy) r2 = owner ? node[2] : 0.0;
             out[0] = r0;
             out[1] = r1;
             out[2] = r2;
@@ -466,6 +474,7 @@ __global__ void __launch_bounds__(SEM_MARCH_MAXT, ModeTraits<MODE>::MINB) sem_ma
 // Host-side launch geometry shared by all instantiations.
 struct MarchGeom {
     int Ty, Mx, pitch, threads;
+    int tp = 0;   // pitch of the top-row side array (v3 kernel only)
     dim3 grid;
 };
 

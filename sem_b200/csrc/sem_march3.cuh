@@ -1,0 +1,710 @@
+// v3 of the fused marching operator (even polynomial orders, all modes): one WARP per strip, TMA-staged inputs,
+// even/odd-folded contractions.
+//
+// Same decomposition as sem_march.cuh (a strip of element rows marches over Mx element columns; x contractions in
+// registers along the march, y contractions through shared memory; owner computes; every value read about once and
+// written exactly once; no atomics).  What changed, and the ncu finding behind each change (profiles/README.md):
+//
+//   * a strip is owned by ONE warp (CTA = 32 threads, EW = 64/P element rows for two node columns per lane).  The lane
+//     that finishes a node column in the x phase and the lanes that contract the element lines above it in the y phase
+//     sit in the same warp, so a step needs two __syncwarp() and no CTA barrier.  v1/v2 and the first v3 lost most of
+//     their issue slots to `stall_barrier` with 2-3 CTAs of 3-5 warps per SM.
+//   * ALL inputs of a marching step -- the contracted fields and both advecting velocity components -- arrive by TMA bulk
+//     copies (cp.async.bulk, one per node line and field, issued by the lanes of the warp, completion on an mbarrier)
+//     into a two-stage ring that is refilled as soon as a stage has been consumed (two steps of loads in flight per
+//     warp).  v1/v2 fetched part of the inputs with LDG inside the step: top stall long_scoreboard, spilled registers.
+//   * even/odd folding: Ks is centro-symmetric and diag(w) D centro-antisymmetric, so with e_k = a_k + a_{P-k},
+//     o_k = a_k - a_{P-k} the rows i and P-i of a contraction share their partial sums E_i, O_i:
+//         (Ks a)_i = E + O, (Ks a)_{P-i} = E - O;   (wD a)_i = E' + O', (wD a)_{P-i} = O' - E'.
+//     81 instead of 162 DFMAs per element line for K and D together, and half as many table operands.
+//   * the folded tables are interleaved (Ke, De | Ko, Do) in constant memory with compile-time offsets, so one LDCU.128
+//     feeds a K and a D partial sum for both columns (lines) of the lane: one uniform table fetch per four DFMAs.
+//   * shared-memory pitches are compile-time constants: every LDS/STS of the step is [register + immediate].
+//   * the top row of every element line goes to a small side array instead of a second colour pass over the accumulator
+//     tile; the consumer adds it when it finishes the shared node (fixed two-term order, bitwise reproducible).
+//   * interior nodes take a branch-free path; boundary rows (O(sqrt N) nodes) are overwritten by a fix-up pass that only
+//     the lanes / steps that touch the boundary execute.  Pointwise Jacobian terms are a template flag (PW).
+//   * the topmost node column of the mesh (NY = ney*P + 1) belongs to the last strip, which holds the remaining
+//     ney mod EW element rows (possibly none): no lane ever handles a 65th column.
+#pragma once
+#include "sem_march.cuh"
+#include "sem_tma.cuh"
+
+#include <type_traits>
+
+namespace semb {
+
+// Folded 1-D tables of order P (P even), rows i = 0 .. P/2.  Row layout (doubles):
+//   pairs k = 0 .. H   : ( Ke[i][k], De[i][k] )     Ke = (Ks[i][k] + Ks[i][P-k]) / 2   (k = H: Ks[i][H]),  same for De from wD
+//   pairs k = 0 .. H-1 : ( Ko[i][k], Do[i][k] )     Ko = (Ks[i][k] - Ks[i][P-k]) / 2
+// with wD[i][k] = w_i D[i][k] (GLL.py:30,45-59,73-81).
+template <int P>
+struct __align__(16) Tab3 {
+    static constexpr int H = P / 2;
+    static constexpr int RS = 2 * (P + 1);
+    double T[(H + 1) * RS];
+};
+template <int P>
+__constant__ Tab3<P> c_tab3;
+
+// NC node columns per lane in the x phase, NL node lines per lane in the y phase (NL >= NC)
+template <int MODE> struct March3Traits { static constexpr int NC = 2, NL = 2; };
+template <> struct March3Traits<MODE_NS> { static constexpr int NC = 1, NL = 1; };
+
+// compile-time geometry of a warp strip
+template <int P, int MODE>
+struct March3Geom {
+    using TR = ModeTraits<MODE>;
+    static constexpr int NC = March3Traits<MODE>::NC, NL = March3Traits<MODE>::NL;
+    static constexpr int EW = (32 * NC / P) > 0 ? (32 * NC / P) : 1;     // element rows per strip
+    static constexpr int NCOLP = (P + EW * P + 1 + 1) & ~1;              // staged columns: halo + own + top node, even
+    static constexpr int PITCH = NCOLP + ((18 - NCOLP % 16) % 16);       // == 2 (mod 16): conflict-free LDS.128 in both phases
+    static constexpr int TPW = (EW + 1 + 1) & ~1;                        // top-row entries per line
+    static constexpr int NSTG = TR::NF + 2 * TR::NV;                     // staged fields: contracted, then U, then V
+    static constexpr int SMEM_DOUBLES = (2 * NSTG + TR::NACC) * P * PITCH + TR::NACC * P * TPW;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 16;
+    static_assert(P % 2 == 0, "v3 needs an even polynomial order");
+    static_assert(EW * P / NC <= 32 && (P / NL) * EW <= 32, "a strip must fit one warp in both phases");
+};
+
+template <int NC>
+struct VecN { double v[NC]; };
+
+template <int NC>
+__device__ __forceinline__ VecN<NC> ld_vec(const double* p) {
+    VecN<NC> r;
+    if constexpr (NC == 2) {
+        const double2 t = *reinterpret_cast<const double2*>(p);
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+    } else {
+        r.v[0] = p[0];
+    }
+    return r;
+}
+
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+template <int P, int MODE, bool PW>
+struct March3 {
+    using MM = March<P, MODE>;
+    using GE = March3Geom<P, MODE>;
+    static constexpr int n = P + 1, H = P / 2;
+    static constexpr int NF = MM::NF, NV = MM::NV, NACC = MM::NACC, NOUT = MM::NOUT;
+    static constexpr int NC = GE::NC, NL = GE::NL, EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, NSTG = GE::NSTG;
+    static constexpr int G = P / NL;   // lanes per element in the y phase
+    static constexpr bool HAS_BC = (MODE == MODE_CD || MODE == MODE_NS);
+    static constexpr bool NODE_FAST = (MODE == MODE_NS) && PW;   // the NS JVP multiplies the node values by pointwise diagonals
+
+    // ---- folded contraction: rows I and P-I of (Ks a) and (wD a) for NV_ vectors at once --------------------------------
+    // sK[0] / sD[0]: row I, sK[1] / sD[1]: row P-I (I < H only).  DIR 0: x phase, 1: y phase (selects the fields needed).
+    template <int I, int DIR, int NV_>
+    static __device__ __forceinline__ void contract(const double (&e)[NV_][NF][H + 1], const double (&o)[NV_][NF][H],
+                                                    double (&sK)[2][NV_][NF], double (&sD)[2][NV_][NF], int z) {
+        // z: always 0, but uniform and loop-variant (see the kernel) -- keeps the table fetches just-in-time LDCUs
+        const double2* __restrict__ t2 = reinterpret_cast<const double2*>(
+            __builtin_assume_aligned(c_tab3<P>.T + I * Tab3<P>::RS + 2 * z, 16));
+        double EK[NV_][NF], ED[NV_][NF], OK[NV_][NF], OD[NV_][NF];
+#pragma unroll
+        for (int v = 0; v < NV_; ++v)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) EK[v][f] = ED[v][f] = OK[v][f] = OD[v][f] = 0.0;
+#pragma unroll
+        for (int k = 0; k <= H; ++k) {
+            const double2 c = t2[k];
+#pragma unroll
+            for (int v = 0; v < NV_; ++v)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const bool nk = DIR == 0 ? MM::x_needs_K(f) : MM::y_needs_K(f);
+                    const bool nd = (DIR == 0 ? MM::x_needs_D(f) : MM::y_needs_D(f)) && I < H;   // De row H is zero
+                    if (nk) EK[v][f] = (k == 0) ? c.x * e[v][f][0] : fma(c.x, e[v][f][k], EK[v][f]);
+                    if (nd) ED[v][f] = (k == 0) ? c.y * e[v][f][0] : fma(c.y, e[v][f][k], ED[v][f]);
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const double2 c = t2[H + 1 + k];
+#pragma unroll
+            for (int v = 0; v < NV_; ++v)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const bool nk = (DIR == 0 ? MM::x_needs_K(f) : MM::y_needs_K(f)) && I < H;   // Ko row H is zero
+                    const bool nd = DIR == 0 ? MM::x_needs_D(f) : MM::y_needs_D(f);
+                    if (nk) OK[v][f] = (k == 0) ? c.x * o[v][f][0] : fma(c.x, o[v][f][k], OK[v][f]);
+                    if (nd) OD[v][f] = (k == 0) ? c.y * o[v][f][0] : fma(c.y, o[v][f][k], OD[v][f]);
+                }
+        }
+#pragma unroll
+        for (int v = 0; v < NV_; ++v)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                sK[0][v][f] = EK[v][f] + OK[v][f];
+                sK[1][v][f] = EK[v][f] - OK[v][f];
+                sD[0][v][f] = ED[v][f] + OD[v][f];
+                sD[1][v][f] = OD[v][f] - ED[v][f];
+            }
+    }
+
+    // fold an element line a[0..P] into its even / odd parts
+    static __device__ __forceinline__ void fold(const double (&a)[n], double (&e)[H + 1], double (&o)[H]) {
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            e[k] = a[k] + a[P - k];
+            o[k] = a[k] - a[P - k];
+        }
+        e[H] = a[H];
+    }
+
+    // ---- per-node combination of the contractions (sD already carries the quadrature weight of its own direction) -------
+    // x phase: wy = assembled y-weight of the column (dy/2 included), ckx = wy * 2/dx, ccw = cconv * wy
+    static __device__ __forceinline__ void xcomb(const double (&sK)[NF], const double (&sD)[NF], double Uc, double ckx,
+                                                 double wy, double ccw, double (&x)[NOUT]) {
+        if constexpr (MODE == MODE_K) {
+            x[0] = ckx * sK[0];
+        } else if constexpr (MODE == MODE_G) {
+            x[0] = ccw * sD[0];
+            x[1] = 0.0;
+        } else if constexpr (MODE == MODE_CD) {
+            x[0] = fma(ccw * Uc, sD[0], ckx * sK[0]);
+        } else if constexpr (MODE == MODE_DIV) {
+            x[0] = wy * sD[0];
+        } else {
+            const double cu = ccw * Uc;
+            x[0] = fma(wy, sD[2], fma(cu, sD[0], ckx * sK[0]));
+            x[1] = fma(cu, sD[1], ckx * sK[1]);
+            x[2] = wy * sD[0];
+        }
+    }
+    // y phase: wx = assembled x-weight of the line (dx/2 included), cky = wx * 2/dy, ccw = cconv * wx
+    static __device__ __forceinline__ void ycomb(const double (&sK)[NF], const double (&sD)[NF], double Vc, double cky,
+                                                 double wx, double ccw, double (&y)[NACC]) {
+        if constexpr (MODE == MODE_K) {
+            y[0] = cky * sK[0];
+        } else if constexpr (MODE == MODE_G) {
+            y[0] = ccw * sD[0];
+        } else if constexpr (MODE == MODE_CD) {
+            y[0] = fma(ccw * Vc, sD[0], cky * sK[0]);
+        } else if constexpr (MODE == MODE_DIV) {
+            y[0] = wx * sD[1];
+        } else {
+            const double cv = ccw * Vc;
+            y[0] = fma(cv, sD[0], cky * sK[0]);
+            y[1] = fma(wx, sD[2], fma(cv, sD[1], cky * sK[1]));
+            y[2] = wx * sD[1];
+        }
+    }
+
+    // ---- one y-phase item: NL lines (slots sp, sp+G, ..) of the element whose node j = 0 sits in tile column col0 -------
+    // FULLROWS: rows 0 .. P-1 -> accumulator tile sA, row P -> sT[line][topslot];  else only row P -> sT[line][topslot].
+    template <bool FULLROWS>
+    static __device__ __forceinline__ void yitem(int sp, int col0, int topslot, const double (&wx)[NL], double cc,
+                                                 double ky, const double* __restrict__ sB, double* __restrict__ sA,
+                                                 double* __restrict__ sT, int z) {
+        double cky[NL], ccw[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            cky[l] = wx[l] * ky;
+            ccw[l] = cc * wx[l];
+        }
+        double e[NL][NF][H + 1], o[NL][NF][H];
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const double* row = sB + (f * P + sp + l * G) * PITCH + col0;
+                double a[n];
+#pragma unroll
+                for (int k = 0; k < P; k += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(row + k);
+                    a[k] = v.x;
+                    a[k + 1] = v.y;
+                }
+                a[P] = row[P];
+                fold(a, e[l][f], o[l][f]);
+            }
+        const double* sV = sB + ((NF + 1) * P + sp) * PITCH + col0;   // V line of slot sp (NV modes)
+        if constexpr (FULLROWS) {
+            double Y[NL][NACC][n];
+            static_for<0, H + 1>([&](auto Jc) {
+                constexpr int J = decltype(Jc)::value;
+                double sK[2][NL][NF], sD[2][NL][NF];
+                contract<J, 1, NL>(e, o, sK, sD, z);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    double Vlo = 0.0, Vhi = 0.0;
+                    if constexpr (NV) {
+                        Vlo = sV[l * G * PITCH + J];
+                        if constexpr (J < H) Vhi = sV[l * G * PITCH + P - J];
+                    }
+                    double y[NACC];
+                    ycomb(sK[0][l], sD[0][l], Vlo, cky[l], wx[l], ccw[l], y);
+#pragma unroll
+                    for (int a = 0; a < NACC; ++a) Y[l][a][J] = y[a];
+                    if constexpr (J < H) {
+                        ycomb(sK[1][l], sD[1][l], Vhi, cky[l], wx[l], ccw[l], y);
+#pragma unroll
+                        for (int a = 0; a < NACC; ++a) Y[l][a][P - J] = y[a];
+                    }
+                }
+            });
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    double* dst = sA + (a * P + sp + l * G) * PITCH + col0;
+#pragma unroll
+                    for (int j = 0; j < P; j += 2)
+                        *reinterpret_cast<double2*>(dst + j) = make_double2(Y[l][a][j], Y[l][a][j + 1]);
+                    sT[(a * P + sp + l * G) * TPW + topslot] = Y[l][a][P];
+                }
+        } else {
+            double sK[2][NL][NF], sD[2][NL][NF];
+            contract<0, 1, NL>(e, o, sK, sD, z);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                double Vhi = 0.0;
+                if constexpr (NV) Vhi = sV[l * G * PITCH + P];
+                double y[NACC];
+                ycomb(sK[1][l], sD[1][l], Vhi, cky[l], wx[l], ccw[l], y);
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) sT[(a * P + sp + l * G) * TPW + topslot] = y[a];
+            }
+        }
+    }
+
+    // ---- y phase over the P staged lines of one buffer ----------------------------------------------------------------------
+    // main pass: lane q < G*nty contracts NL lines of element q / G (slots q % G, ..); halo pass: lanes q < G evaluate the
+    // top row of the element below the strip (its node j = 0 is tile column 0) -> sT[line][0].  wx: x-weights of the
+    // slots (lane % G) + l*G -- the same for both passes because q < G implies q % G == q.
+    static __device__ __forceinline__ void yphase(int nty, int halo, const double (&wx)[NL], double cc, double ky,
+                                                  const double* __restrict__ sB, double* __restrict__ sA,
+                                                  double* __restrict__ sT, int z) {
+        const int q = threadIdx.x;
+        if (q < G * nty) yitem<true>(q % G, halo + (q / G) * P, q / G + 1, wx, cc, ky, sB, sA, sT, z);
+        if (halo > 0 && q < G) yitem<false>(q, 0, 0, wx, cc, ky, sB, sA, sT, z);
+    }
+
+    // store the NOUT outputs of the lane's NC nodes of line ix
+    static __device__ __forceinline__ void store(const MeshDev& g, const MarchArgs& A, int ix, int iy0,
+                                                 const bool (&own)[NC], const double (&out)[NC][NOUT]) {
+        const int off = ix * g.LD + iy0;
+        double* const y[3] = {A.y0, A.y1, A.y2};
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+            if (MODE == MODE_G && !y[o]) continue;
+            if constexpr (NC == 2) {
+                if (own[1]) {
+                    *reinterpret_cast<double2*>(y[o] + off) = make_double2(out[0][o], out[1][o]);   // 16-byte aligned
+                } else if (own[0]) {
+                    y[o][off] = out[0][o];
+                }
+            } else {
+                if (own[0]) y[o][off] = out[0][o];
+            }
+        }
+    }
+
+    // interior path: element sums + pointwise terms, no boundary logic
+    static __device__ __forceinline__ void finalize_fast(const MeshDev& g, const MarchArgs& A, int ix, int iy0,
+                                                         const bool (&own)[NC], const double (&xp)[NC][NOUT],
+                                                         const double (&yp)[NC][NACC], const double (&node)[NC][NF],
+                                                         const double (&wyA)[NC]) {
+        double out[NC][NOUT];
+        double wxl = 0.0;
+        if constexpr (MODE == MODE_NS && PW) wxl = 0.5 * g.dx * asm_weight<P>(ix, g.nex);   // buoyancy term only
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            MM::template finish_vals<true, PW>(g, A, ix, iy0 + c, xp[c], yp[c], node[c], wxl, wyA[c], out[c]);
+        store(g, A, ix, iy0, own, out);
+    }
+
+    // general path (last line of the slab: Dirichlet E line, interface line of a partition)
+    static __device__ __forceinline__ void finalize_slow(const MeshDev& g, const MarchArgs& A, int ix, int iy0,
+                                                         const bool (&own)[NC], const double (&xp)[NC][NOUT],
+                                                         const double (&yp)[NC][NACC], const double (&node)[NC][NF],
+                                                         const double (&wyA)[NC]) {
+        double out[NC][NOUT];
+        const double wxl = 0.5 * g.dx * asm_weight<P>(ix, g.nex);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            MM::template finish_vals<false, true>(g, A, ix, iy0 + c, xp[c], yp[c], node[c], wxl, wyA[c], out[c]);
+        store(g, A, ix, iy0, own, out);
+    }
+
+    // Boundary rows of the lines m*P .. m*P+P-1 at the lane's columns: Dirichlet rows (x - value, or x in JVP form) and the
+    // pressure pin overwrite what the interior path stored (same thread, same address: program order).  Only lanes on
+    // the S/N boundary columns, the step that holds the W line and the step that holds the pin line get here.
+    static __device__ __noinline__ void bc_fixup(const MeshDev& g, const MarchArgs& A, int m, int iy0, int c0, bool own0,
+                                                 bool own1, const double* __restrict__ sB, const double* aprev) {
+        for (int R = 0; R < P; ++R) {
+            const int ix = m * P + R, gix = g.gx0 + ix;
+            for (int c = 0; c < NC; ++c) {
+                if (!(c == 0 ? own0 : own1)) continue;
+                const int iy = iy0 + c;
+                const int side = bc_side(A.bc, gix, iy, g.NXg, g.NY);
+                const bool pin = (MODE == MODE_NS) && gix == A.bc.pin_gx && iy == A.bc.pin_iy;
+                if (side < 0 && !pin) continue;
+                const int off = ix * g.LD + iy;
+                double nv[NF];
+                for (int f = 0; f < NF; ++f) nv[f] = (R == 0) ? aprev[c * NF + f] : sB[(f * P + R - 1) * PITCH + c0 + c];
+                if (side >= 0) {
+                    A.y0[off] = nv[0] - (A.bc.residual ? A.bc.val0[side] : 0.0);
+                    if constexpr (MODE == MODE_NS) A.y1[off] = nv[1] - (A.bc.residual ? A.bc.val1[side] : 0.0);
+                }
+                if constexpr (MODE == MODE_NS) {
+                    if (pin) A.y2[off] = nv[2];
+                }
+            }
+        }
+    }
+
+    // ---- x phase of one element column for the NC node columns of the lane -------------------------------------------------------
+    // FULL: element m (lines m*P .. m*P+P): finishes and stores lines m*P .. m*P+P-1, leaves the x-part of line (m+1)*P
+    //       in xc, its y-part in yc, its node values in a0 and its U in U0.
+    // !FULL (prologue of a chunk that does not start at the left edge): only the carries are produced.
+    // On entry a0 = node values of the first line of the element; the other P lines are the rows of the stage sB.
+    template <bool FULL>
+    static __device__ __forceinline__ void xphase(const MeshDev& g, const MarchArgs& A, int m, int iy0, int c0, int topi,
+                                                  const bool (&own)[NC], bool colflag, const double* __restrict__ sB,
+                                                  const double* __restrict__ sA, const double* __restrict__ sT,
+                                                  const double (&wyA)[NC], double cc, double (&a0)[NC][NF],
+                                                  double (&U0)[NC], double (&xc)[NC][NOUT], double (&yc)[NC][NACC], int z) {
+        double ckx[NC], ccw[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            ckx[c] = wyA[c] * (2.0 / g.dx);
+            ccw[c] = cc * wyA[c];
+        }
+        double e[NC][NF][H + 1], o[NC][NF][H];
+        double aprev[NC][NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            double a[NC][n];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                a[c][0] = a0[c][f];
+                aprev[c][f] = a0[c][f];
+            }
+#pragma unroll
+            for (int k = 1; k <= P; ++k) {
+                const VecN<NC> v = ld_vec<NC>(sB + (f * P + (k - 1)) * PITCH + c0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) a[c][k] = v.v[c];
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                a0[c][f] = a[c][P];
+                fold(a[c], e[c][f], o[c][f]);
+            }
+        }
+        // y-part / U / node values of line m*P + R (R >= 1) at the lane's columns
+        auto load_y = [&](int R, double (&yp)[NC][NACC]) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                const VecN<NC> v = ld_vec<NC>(sA + (a * P + (R - 1)) * PITCH + c0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) yp[c][a] = v.v[c];
+                if (topi >= 0) yp[0][a] += sT[(a * P + (R - 1)) * TPW + topi];   // only the first column can be a shared node
+            }
+        };
+        auto load_U = [&](int R, double (&Uc)[NC]) {
+            if constexpr (NV) {
+                const VecN<NC> v = ld_vec<NC>(sB + (NF * P + (R - 1)) * PITCH + c0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) Uc[c] = v.v[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) Uc[c] = 0.0;
+            }
+        };
+        auto load_node = [&](int R, double (&node)[NC][NF]) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) node[c][f] = 0.0;
+                if constexpr (NODE_FAST) {
+                    const VecN<NC> v = ld_vec<NC>(sB + (f * P + (R - 1)) * PITCH + c0);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) node[c][f] = v.v[c];
+                }
+            }
+        };
+
+        static_for<0, (FULL ? H + 1 : 1)>([&](auto Ic) {
+            constexpr int I = decltype(Ic)::value;
+            double sK[2][NC][NF], sD[2][NC][NF];
+            contract<I, 0, NC>(e, o, sK, sD, z);
+            if constexpr (FULL) {   // row I
+                const int ix = m * P + I;
+                double Uc[NC], xp[NC][NOUT], yp[NC][NACC], node[NC][NF];
+                if constexpr (I == 0) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) Uc[c] = U0[c];
+                } else {
+                    load_U(I, Uc);
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) xcomb(sK[0][c], sD[0][c], Uc[c], ckx[c], wyA[c], ccw[c], xp[c]);
+                if constexpr (I == 0) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                        for (int q = 0; q < NOUT; ++q) xp[c][q] += xc[c][q];
+#pragma unroll
+                        for (int q = 0; q < NACC; ++q) yp[c][q] = yc[c][q];
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) node[c][f] = aprev[c][f];
+                    }
+                } else {
+                    load_y(I, yp);
+                    load_node(I, node);
+                }
+                finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA);
+            }
+            if constexpr (I < H) {   // row P - I
+                constexpr int R = P - I;
+                double Uc[NC], xp[NC][NOUT];
+                load_U(R, Uc);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) xcomb(sK[1][c], sD[1][c], Uc[c], ckx[c], wyA[c], ccw[c], xp[c]);
+                if constexpr (I == 0) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                        for (int q = 0; q < NOUT; ++q) xc[c][q] = xp[c][q];
+                        U0[c] = Uc[c];
+                    }
+                } else {
+                    const int ix = m * P + R;
+                    double yp[NC][NACC], node[NC][NF];
+                    load_y(R, yp);
+                    load_node(R, node);
+                    finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA);
+                }
+            }
+        });
+        load_y(P, yc);
+        if constexpr (FULL && HAS_BC) {
+            const int gl = g.gx0 + m * P;
+            const bool fix = colflag || gl == 0 || (MODE == MODE_NS && (unsigned)(A.bc.pin_gx - gl) < (unsigned)P);
+            if (fix) bc_fixup(g, A, m, iy0, c0, own[0], own[NC - 1], sB, &aprev[0][0]);
+        }
+    }
+};
+
+template <int P, int MODE, bool PW>
+__global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ MeshDev g, const __grid_constant__ MarchArgs A,
+                                                        const int Mx) {
+    using M3 = March3<P, MODE, PW>;
+    using GE = March3Geom<P, MODE>;
+    constexpr int NF = M3::NF, NACC = M3::NACC, NOUT = M3::NOUT, NSTG = M3::NSTG, NC = M3::NC, NL = M3::NL, G = M3::G;
+    constexpr int EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW;
+    constexpr int STAGE = NSTG * P * PITCH;               // doubles per stage
+    extern __shared__ __align__(16) double smem3[];
+    double* sS = smem3;                                   // [2][NSTG][P][PITCH] staged node lines (TMA destination)
+    double* sA = sS + 2 * STAGE;                          // [NACC][P][PITCH]    y-part rows 0..P-1 of every element line
+    double* sT = sA + NACC * P * PITCH;                   // [NACC][P][TPW]      y-part row P (node shared with the element above)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT + NACC * P * TPW);   // [2]
+
+    const int lane = threadIdx.x;
+    const int n0 = blockIdx.x * EW;
+    const int nty = max(0, min(EW, g.ney - n0));          // the last strip holds the remaining ney % EW rows (maybe none)
+    const bool last_strip = (blockIdx.x == gridDim.x - 1);
+    const int m0 = blockIdx.y * Mx;
+    const int m1 = min(m0 + Mx, g.nex);
+    const int halo = (n0 > 0) ? P : 0;
+    const int ybase = n0 * P - halo;                      // even
+    const int ncolp = (halo + nty * P + 1 + 1) & ~1;      // staged columns per line (even)
+    const int nown = nty * P + (last_strip ? 1 : 0);      // the strip owns tile columns halo .. halo + nown - 1
+    const int cr = NC * lane;                             // first own column of this lane (relative)
+    const int c0 = halo + cr;                             // ... in the staged tile
+    const int iy0 = ybase + c0;
+    const bool xthr = cr < nown;
+    bool own[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) own[c] = cr + c < nown;
+    const int topi = (xthr && cr % P == 0) ? cr / P : -1;
+    const double cc = A.cconv;
+    const double ky = 2.0 / g.dy;
+    const uint32_t line_bytes = (uint32_t)ncolp * 8u;
+
+    // staged field f (a compare-select chain: a pointer array indexed at run time would live in local memory)
+    auto field = [&](int f) -> const double* {
+        const double* p = A.a;
+        if (NF > 1 && f == 1) p = A.b;
+        if (NF > 2 && f == 2) p = A.c;
+        if (M3::NV && f == NF) p = A.U;
+        if (M3::NV && f == NF + 1) p = A.V;
+        return p;
+    };
+
+    double wyA[NC];
+    bool colflag = false;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        wyA[c] = own[c] ? 0.5 * g.dy * asm_weight<P>(iy0 + c, g.ney) : 0.0;
+        colflag = colflag || (own[c] && (iy0 + c == 0 || iy0 + c == g.NY - 1 || (MODE == MODE_NS && iy0 + c == A.bc.pin_iy)));
+    }
+    // x-weights of the y-phase slots of this lane: interior lines of an element column, the same in every step except
+    // for the last slot of the last column of the mesh (no element to its right)
+    const int sp = lane % G;
+    double wx_in[NL], wx_end[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const int slot = sp + l * G;
+        wx_in[l] = 0.5 * g.dx * (slot == P - 1 ? c_tab<P>.w[P] + c_tab<P>.w[0] : c_tab<P>.w[slot + 1]);
+        wx_end[l] = 0.5 * g.dx * (slot == P - 1 ? c_tab<P>.w[P] : c_tab<P>.w[slot + 1]);
+    }
+
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    // the accumulator column of the topmost mesh node and the halo entry of sT are never written by the y phase
+    for (int i = lane; i < NACC * P * (PITCH + TPW); i += 32) sA[i] = 0.0;
+    __syncwarp();
+
+    // the lanes issue the bulk copies of `nlines` node lines of every staged field into buffer `buf`, one copy per lane
+    auto issue = [&](int buf, int line_first, int nlines, int slot_first) {
+        if (lane == 0) mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
+        __syncwarp();
+        for (int i = lane; i < NSTG * nlines; i += 32) {
+            const int f = i / nlines, k = i - f * nlines;
+            bulk_g2s(sS + buf * STAGE + (f * P + slot_first + k) * PITCH,
+                     field(f) + (size_t)(line_first + k) * g.LD + ybase, line_bytes, &bar[buf]);
+        }
+    };
+
+    double a0[NC][NF], U0[NC], xc[NC][NOUT], yc[NC][NACC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        U0[c] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NOUT; ++q) xc[c][q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) yc[c][q] = 0.0;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) a0[c][f] = 0.0;
+    }
+
+    // ---- prologue: carries of line m0*P (x-part from the element on the left, y-part from a y phase over its lines) -------
+    {
+        const int ix = m0 * P;
+        if (m0 > 0) issue(1, ix - P + 1, P, 0);   // lines (m0-1)P+1 .. m0*P -> slots 0 .. P-1
+        else issue(1, 0, 1, P - 1);               // line 0 -> slot P-1 (the other slots hold stale values, results unused)
+        issue(0, ix + 1, P, 0);                   // first marching step
+        if (xthr && m0 > 0) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const VecN<NC> v = ld_vec<NC>(field(f) + (size_t)(ix - P) * g.LD + iy0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) a0[c][f] = v.v[c];
+            }
+        }
+        double wx[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) wx[l] = 0.5 * g.dx * asm_weight<P>(ix - P + 1 + sp + l * G, g.nex);
+        mbar_wait(&bar[1], 0);
+        const double* sB = sS + STAGE;
+        M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, m0 >> 30);
+        __syncwarp();
+        if (xthr) {
+            if (m0 > 0) {
+                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc,
+                                           m0 >> 30);
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const VecN<NC> v = ld_vec<NC>(sB + (f * P + (P - 1)) * PITCH + c0);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) a0[c][f] = v.v[c];
+                }
+                if constexpr (M3::NV) {
+                    const VecN<NC> v = ld_vec<NC>(sB + (NF * P + (P - 1)) * PITCH + c0);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) U0[c] = v.v[c];
+                }
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    const VecN<NC> v = ld_vec<NC>(sA + (a * P + (P - 1)) * PITCH + c0);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) yc[c][a] = v.v[c];
+                    if (topi >= 0) yc[0][a] += sT[(a * P + (P - 1)) * TPW + topi];
+                }
+            }
+        }
+        __syncwarp();   // buffer 1 and the accumulators are free again
+        if (m0 + 1 < m1) issue(1, (m0 + 1) * P + 1, P, 0);
+    }
+
+    // ---- march --------------------------------------------------------------------------------------------------------------------
+    uint32_t ph0 = 0, ph1 = 1;
+    for (int m = m0; m < m1; ++m) {
+        const int b = (m - m0) & 1;
+        if (b == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; }
+        const double* sB = sS + b * STAGE;
+        double wx[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) wx[l] = (m + 1 == g.nex) ? wx_end[l] : wx_in[l];
+        // z == 0 (m < 2^30), but the compiler cannot prove it: uniform and different in every trip, so the constant-table
+        // fetches stay LDCUs next to their DFMAs instead of being hoisted into ~100 registers (and R2UR'd back)
+        const int z = m >> 30;
+        M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, z);
+        __syncwarp();
+        if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, z);
+        __syncwarp();   // buffer b and the accumulators are free: refill the buffer with the lines of step m + 2
+        if (m + 2 < m1) issue(b, (m + 2) * P + 1, P, 0);
+    }
+
+    // ---- epilogue: the last line of the slab has no element to its right ---------------------------------------------------------
+    if (xthr && m1 == g.nex) M3::finalize_slow(g, A, g.nex * P, iy0, own, xc, yc, a0, wyA);
+}
+
+// host mirror of the compile-time geometry
+struct March3Shape { int nc, nl, nstg, nacc; };
+inline March3Shape march3_shape(int mode) {
+    switch (mode) {
+        case MODE_K: return {2, 2, 1, 1};
+        case MODE_G: return {2, 2, 1, 1};
+        case MODE_DIV: return {2, 2, 2, 1};
+        case MODE_CD: return {2, 2, 3, 1};
+        default: return {1, 1, 5, 3};
+    }
+}
+
+// grid: x = strips of EW element rows (+ the last strip with the remainder and the topmost node column), y = chunks of Mx
+// element columns.  Mx: enough chunks for ~3 resident rounds of the device, chunks of at least 8 columns (the x-halo
+// costs 1/Mx extra reads and one extra y phase per chunk).
+inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_count, size_t smem_bytes, size_t smem_sm) {
+    MarchGeom q;
+    const March3Shape s = march3_shape(mode);
+    const int EW = (32 * s.nc / g.P) > 0 ? (32 * s.nc / g.P) : 1;
+    const int strips = g.ney / EW + 1;
+    int resident = (int)(smem_sm / (smem_bytes + 1024));
+    if (resident > 32) resident = 32;
+    if (resident < 1) resident = 1;
+    int Mx = Mx_req;
+    if (Mx <= 0) {
+        const long long slots = (long long)sm_count * resident;
+        const int want = (int)((3 * slots + strips - 1) / strips);   // ~3 rounds
+        Mx = (g.nex + want - 1) / want;
+        if (Mx < 8) Mx = 8;
+    }
+    if (Mx > g.nex) Mx = g.nex;
+    q.Ty = EW;
+    q.Mx = Mx;
+    q.pitch = 0;
+    q.threads = 32;
+    q.grid = dim3((unsigned)strips, (unsigned)((g.nex + Mx - 1) / Mx), 1);
+    return q;
+}
+
+}  // namespace semb

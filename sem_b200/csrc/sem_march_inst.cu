@@ -2,6 +2,8 @@
 // parallel.  Exposes a launcher and a table uploader for that order through the registry in sem_dispatch.h.
 #include "sem_march.cuh"
 #include "sem_march2.cuh"
+#include "sem_march3.cuh"
+#include <cmath>
 #include "sem_dispatch.h"
 
 #ifndef SEM_P
@@ -68,6 +70,93 @@ int SEM_CAT(march2_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs&
     }
 #endif
     return 1;
+}
+
+// ---- v3 kernel (one warp per strip, TMA-staged, folded tables): even orders, all modes.  Returns 1 when not available.
+#if SEM_P % 2 == 0
+template <int P, int MODE, bool PW>
+static int launch_mode3(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
+    constexpr size_t smem = March3Geom<P, MODE>::SMEM_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        if (smem > 48 * 1024)
+            SEM_CUDA(cudaFuncSetAttribute(sem_march3_kernel<P, MODE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    sem_march3_kernel<P, MODE, PW><<<q.grid, 32, smem, st>>>(g, A, q.Mx);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+#endif
+
+int SEM_CAT(march3_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q,
+                                    cudaStream_t st) {
+#if SEM_P % 2 == 0
+    switch (mode) {
+        case MODE_K: return launch_mode3<SEM_P, MODE_K, false>(g, A, q, st);
+        case MODE_G: return launch_mode3<SEM_P, MODE_G, false>(g, A, q, st);
+        case MODE_DIV: return launch_mode3<SEM_P, MODE_DIV, false>(g, A, q, st);
+        case MODE_CD:
+            return (A.e0 || A.e1) ? launch_mode3<SEM_P, MODE_CD, true>(g, A, q, st)
+                                  : launch_mode3<SEM_P, MODE_CD, false>(g, A, q, st);
+        case MODE_NS:
+            return (A.d0 || A.e0) ? launch_mode3<SEM_P, MODE_NS, true>(g, A, q, st)
+                                  : launch_mode3<SEM_P, MODE_NS, false>(g, A, q, st);
+    }
+#endif
+    return 1;
+}
+
+// shared memory per CTA (= warp) of the v3 kernel of a mode, 0 when there is none
+size_t SEM_CAT(march3_smem_p, SEM_P)(int mode) {
+#if SEM_P % 2 == 0
+    switch (mode) {
+        case MODE_K: return March3Geom<SEM_P, MODE_K>::SMEM_BYTES;
+        case MODE_G: return March3Geom<SEM_P, MODE_G>::SMEM_BYTES;
+        case MODE_DIV: return March3Geom<SEM_P, MODE_DIV>::SMEM_BYTES;
+        case MODE_CD: return March3Geom<SEM_P, MODE_CD>::SMEM_BYTES;
+        case MODE_NS: return March3Geom<SEM_P, MODE_NS>::SMEM_BYTES;
+    }
+#endif
+    return 0;
+}
+
+// Folded tables of the v3 kernel (layout: Tab3 in sem_march3.cuh).  The folding relies on Ks being centro-symmetric and
+// diag(w) D centro-antisymmetric; the tables handed in are checked for it (they are, for GLL nodes: GLL.py:22-59).
+int SEM_CAT(upload_tab3_p, SEM_P)(const double* D, const double* Ks, const double* w) {
+#if SEM_P % 2 == 0
+    constexpr int P = SEM_P, H = P / 2, n = P + 1, RS = Tab3<P>::RS;
+    double scaleK = 0.0, scaleD = 0.0, asym = 0.0;
+    for (int i = 0; i < n * n; ++i) {
+        scaleK = std::fmax(scaleK, std::fabs(Ks[i]));
+        scaleD = std::fmax(scaleD, std::fabs(D[i]));
+    }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < n; ++k) {
+            asym = std::fmax(asym, std::fabs(Ks[i * n + k] - Ks[(P - i) * n + (P - k)]) / scaleK);
+            asym = std::fmax(asym, std::fabs(w[i] * D[i * n + k] + w[P - i] * D[(P - i) * n + (P - k)]) / scaleD);
+        }
+    if (!(asym < 1e-12)) {
+        set_error("upload_tab3: the GLL tables are not centro-(anti)symmetric to 1e-12; the folded kernel cannot use them");
+        return -2;
+    }
+    Tab3<P> h;
+    for (int i = 0; i <= H; ++i) {
+        double* row = h.T + i * RS;
+        for (int k = 0; k <= H; ++k) {
+            const double ka = Ks[i * n + k], kb = Ks[i * n + (P - k)];
+            const double da = w[i] * D[i * n + k], db = w[i] * D[i * n + (P - k)];
+            row[2 * k] = (k == H) ? ka : 0.5 * (ka + kb);
+            row[2 * k + 1] = (k == H) ? da : 0.5 * (da + db);
+            if (k < H) {
+                row[2 * (H + 1 + k)] = 0.5 * (ka - kb);
+                row[2 * (H + 1 + k) + 1] = 0.5 * (da - db);
+            }
+        }
+    }
+    SEM_CUDA(cudaMemcpyToSymbol(c_tab3<P>, &h, sizeof(h)));
+#endif
+    return 0;
 }
 
 size_t SEM_CAT(march2_smem_p, SEM_P)(int mode, int pitch) {
