@@ -32,6 +32,11 @@
 
 #include <type_traits>
 
+#ifndef SEM_V3_CONV
+#define SEM_V3_CONV 0   // A/B switch. bit 0: y phase, bit 1: x phase run convergent (all lanes compute, stores guarded).
+                        // Measured at config 5 (B200): 0 is fastest for CD (0.39 ms vs 0.48-0.50) and NS; K is indifferent.
+#endif
+
 namespace semb {
 
 // Folded 1-D tables of order P (P even), rows i = 0 .. P/2.  Row layout (doubles):
@@ -101,6 +106,7 @@ struct March3 {
     static constexpr int G = P / NL;   // lanes per element in the y phase
     static constexpr bool HAS_BC = (MODE == MODE_CD || MODE == MODE_NS);
     static constexpr bool NODE_FAST = (MODE == MODE_NS) && PW;   // the NS JVP multiplies the node values by pointwise diagonals
+    static constexpr int NPD = NODE_FAST ? 4 : 1;                // pointwise diagonals prefetched into registers per node
 
     // ---- folded contraction: rows I and P-I of (Ks a) and (wD a) for NV_ vectors at once --------------------------------
     // sK[0] / sD[0]: row I, sK[1] / sD[1]: row P-I (I < H only).  DIR 0: x phase, 1: y phase (selects the fields needed).
@@ -203,8 +209,9 @@ struct March3 {
 
     // ---- one y-phase item: NL lines (slots sp, sp+G, ..) of the element whose node j = 0 sits in tile column col0 -------
     // FULLROWS: rows 0 .. P-1 -> accumulator tile sA, row P -> sT[line][topslot];  else only row P -> sT[line][topslot].
+    // Every lane computes (convergent code keeps the table fetches on the uniform datapath); `active` guards the stores.
     template <bool FULLROWS>
-    static __device__ __forceinline__ void yitem(int sp, int col0, int topslot, const double (&wx)[NL], double cc,
+    static __device__ __forceinline__ void yitem(bool active, int sp, int col0, int topslot, const double (&wx)[NL], double cc,
                                                  double ky, const double* __restrict__ sB, double* __restrict__ sA,
                                                  double* __restrict__ sT, int z) {
         double cky[NL], ccw[NL];
@@ -254,16 +261,18 @@ struct March3 {
                     }
                 }
             });
+            if (active) {
 #pragma unroll
-            for (int l = 0; l < NL; ++l)
+                for (int l = 0; l < NL; ++l)
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) {
-                    double* dst = sA + (a * P + sp + l * G) * PITCH + col0;
+                    for (int a = 0; a < NACC; ++a) {
+                        double* dst = sA + (a * P + sp + l * G) * PITCH + col0;
 #pragma unroll
-                    for (int j = 0; j < P; j += 2)
-                        *reinterpret_cast<double2*>(dst + j) = make_double2(Y[l][a][j], Y[l][a][j + 1]);
-                    sT[(a * P + sp + l * G) * TPW + topslot] = Y[l][a][P];
-                }
+                        for (int j = 0; j < P; j += 2)
+                            *reinterpret_cast<double2*>(dst + j) = make_double2(Y[l][a][j], Y[l][a][j + 1]);
+                        sT[(a * P + sp + l * G) * TPW + topslot] = Y[l][a][P];
+                    }
+            }
         } else {
             double sK[2][NL][NF], sD[2][NL][NF];
             contract<0, 1, NL>(e, o, sK, sD, z);
@@ -273,8 +282,10 @@ struct March3 {
                 if constexpr (NV) Vhi = sV[l * G * PITCH + P];
                 double y[NACC];
                 ycomb(sK[1][l], sD[1][l], Vhi, cky[l], wx[l], ccw[l], y);
+                if (active) {
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) sT[(a * P + sp + l * G) * TPW + topslot] = y[a];
+                    for (int a = 0; a < NACC; ++a) sT[(a * P + sp + l * G) * TPW + topslot] = y[a];
+                }
             }
         }
     }
@@ -287,8 +298,15 @@ struct March3 {
                                                   const double* __restrict__ sB, double* __restrict__ sA,
                                                   double* __restrict__ sT, int z) {
         const int q = threadIdx.x;
-        if (q < G * nty) yitem<true>(q % G, halo + (q / G) * P, q / G + 1, wx, cc, ky, sB, sA, sT, z);
-        if (halo > 0 && q < G) yitem<false>(q, 0, 0, wx, cc, ky, sB, sA, sT, z);
+        const int sp = q % G;
+        const int nn = (q / G < EW) ? q / G : EW - 1;   // lanes beyond the strip recompute the last element (no stores)
+#if SEM_V3_CONV & 1
+        yitem<true>(q < G * nty, sp, halo + nn * P, nn + 1, wx, cc, ky, sB, sA, sT, z);
+        if (halo > 0) yitem<false>(q < G, sp, 0, 0, wx, cc, ky, sB, sA, sT, z);
+#else
+        if (q < G * nty) yitem<true>(true, sp, halo + nn * P, nn + 1, wx, cc, ky, sB, sA, sT, z);
+        if (halo > 0 && q < G) yitem<false>(true, sp, 0, 0, wx, cc, ky, sB, sA, sT, z);
+#endif
     }
 
     // store the NOUT outputs of the lane's NC nodes of line ix
@@ -311,17 +329,29 @@ struct March3 {
         }
     }
 
-    // interior path: element sums + pointwise terms, no boundary logic
+    // interior path: element sums + pointwise terms, no boundary logic.  pd: the NS Jacobian diagonals of this node
+    // (Re G_x u, Re G_y u, Re G_x v, Re G_y v), fetched into registers at the top of the step (zeros when absent).
     static __device__ __forceinline__ void finalize_fast(const MeshDev& g, const MarchArgs& A, int ix, int iy0,
                                                          const bool (&own)[NC], const double (&xp)[NC][NOUT],
                                                          const double (&yp)[NC][NACC], const double (&node)[NC][NF],
-                                                         const double (&wyA)[NC]) {
+                                                         const double (&wyA)[NC], const double (&pd)[NC][NPD]) {
         double out[NC][NOUT];
-        double wxl = 0.0;
-        if constexpr (MODE == MODE_NS && PW) wxl = 0.5 * g.dx * asm_weight<P>(ix, g.nex);   // buoyancy term only
+        if constexpr (NODE_FAST) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-            MM::template finish_vals<true, PW>(g, A, ix, iy0 + c, xp[c], yp[c], node[c], wxl, wyA[c], out[c]);
+            for (int c = 0; c < NC; ++c) {
+                MM::template finish_vals<true, false>(g, A, ix, iy0 + c, xp[c], yp[c], node[c], 0.0, wyA[c], out[c]);
+                out[c][0] = fma(pd[c][0], node[c][0], fma(pd[c][1], node[c][1], out[c][0]));
+                out[c][1] = fma(pd[c][2], node[c][0], fma(pd[c][3], node[c][1], out[c][1]));
+                if (A.e0) {   // buoyancy -(Gr/Re) M T (residual / coupled JVP only, not in the Krylov loop)
+                    const double wxl = 0.5 * g.dx * asm_weight<P>(ix, g.nex);
+                    out[c][1] = fma(A.cbuoy * (wxl * wyA[c]), A.e0[ix * g.LD + iy0 + c], out[c][1]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                MM::template finish_vals<true, PW>(g, A, ix, iy0 + c, xp[c], yp[c], node[c], 0.0, wyA[c], out[c]);
+        }
         store(g, A, ix, iy0, own, out);
     }
 
@@ -375,7 +405,8 @@ struct March3 {
                                                   const bool (&own)[NC], bool colflag, const double* __restrict__ sB,
                                                   const double* __restrict__ sA, const double* __restrict__ sT,
                                                   const double (&wyA)[NC], double cc, double (&a0)[NC][NF],
-                                                  double (&U0)[NC], double (&xc)[NC][NOUT], double (&yc)[NC][NACC], int z) {
+                                                  double (&U0)[NC], double (&xc)[NC][NOUT], double (&yc)[NC][NACC],
+                                                  const double (&pd)[P][NC][NPD], int z) {
         double ckx[NC], ccw[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
@@ -466,7 +497,7 @@ struct March3 {
                     load_y(I, yp);
                     load_node(I, node);
                 }
-                finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA);
+                finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA, pd[I]);
             }
             if constexpr (I < H) {   // row P - I
                 constexpr int R = P - I;
@@ -486,7 +517,7 @@ struct March3 {
                     double yp[NC][NACC], node[NC][NF];
                     load_y(R, yp);
                     load_node(R, node);
-                    finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA);
+                    finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA, pd[R]);
                 }
             }
         });
@@ -572,15 +603,20 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     for (int i = lane; i < NACC * P * (PITCH + TPW); i += 32) sA[i] = 0.0;
     __syncwarp();
 
-    // the lanes issue the bulk copies of `nlines` node lines of every staged field into buffer `buf`, one copy per lane
+    // one elected lane issues the bulk copies of node lines line_first .. line_first + nlines - 1 of every staged field into slots
+    // slot_first .. of buffer `buf`.  (One copy per lane does not parallelise: UBLKCP is a uniform-datapath instruction
+    // and the compiler serialises the lanes with an ELECT loop, ~10 instructions per copy.)
     auto issue = [&](int buf, int line_first, int nlines, int slot_first) {
-        if (lane == 0) mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
-        __syncwarp();
-        for (int i = lane; i < NSTG * nlines; i += 32) {
-            const int f = i / nlines, k = i - f * nlines;
-            bulk_g2s(sS + buf * STAGE + (f * P + slot_first + k) * PITCH,
-                     field(f) + (size_t)(line_first + k) * g.LD + ybase, line_bytes, &bar[buf]);
+        if (elect_one()) {
+            mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
+#pragma unroll
+            for (int f = 0; f < NSTG; ++f) {
+                const double* src = field(f) + (size_t)line_first * g.LD + ybase;
+                double* dst = sS + buf * STAGE + (f * P + slot_first) * PITCH;
+                for (int k = 0; k < nlines; ++k) bulk_g2s(dst + k * PITCH, src + (size_t)k * g.LD, line_bytes, &bar[buf]);
+            }
         }
+        __syncwarp();
     };
 
     double a0[NC][NF], U0[NC], xc[NC][NOUT], yc[NC][NACC];
@@ -594,6 +630,16 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
 #pragma unroll
         for (int f = 0; f < NF; ++f) a0[c][f] = 0.0;
     }
+
+    // Jacobian diagonals of the lines a step finishes (NS JVP): loaded at the top of the step, consumed after the y phase
+    constexpr int NPD = M3::NPD;
+    double pd[P][NC][NPD];
+#pragma unroll
+    for (int R = 0; R < P; ++R)
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < NPD; ++k) pd[R][c][k] = 0.0;
 
     // ---- prologue: carries of line m0*P (x-part from the element on the left, y-part from a y phase over its lines) -------
     {
@@ -618,7 +664,7 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         __syncwarp();
         if (xthr) {
             if (m0 > 0) {
-                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc,
+                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd,
                                            m0 >> 30);
             } else {
 #pragma unroll
@@ -649,6 +695,19 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     uint32_t ph0 = 0, ph1 = 1;
     for (int m = m0; m < m1; ++m) {
         const int b = (m - m0) & 1;
+        if constexpr (M3::NODE_FAST) {
+            if (A.d0 && xthr) {
+                const double* const dp[4] = {A.d0, A.d1, A.d2, A.d3};
+#pragma unroll
+                for (int R = 0; R < P; ++R)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const VecN<NC> v = ld_vec<NC>(dp[k] + (size_t)(m * P + R) * g.LD + iy0);
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) pd[R][c][k] = v.v[c];
+                    }
+            }
+        }
         if (b == 0) { mbar_wait(&bar[0], ph0); ph0 ^= 1; } else { mbar_wait(&bar[1], ph1); ph1 ^= 1; }
         const double* sB = sS + b * STAGE;
         double wx[NL];
@@ -659,7 +718,11 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         const int z = m >> 30;
         M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, z);
         __syncwarp();
-        if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, z);
+#if SEM_V3_CONV & 2
+        M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
+#else
+        if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
+#endif
         __syncwarp();   // buffer b and the accumulators are free: refill the buffer with the lines of step m + 2
         if (m + 2 < m1) issue(b, (m + 2) * P + 1, P, 0);
     }
@@ -681,8 +744,7 @@ inline March3Shape march3_shape(int mode) {
 }
 
 // grid: x = strips of EW element rows (+ the last strip with the remainder and the topmost node column), y = chunks of Mx
-// element columns.  Mx: enough chunks for ~3 resident rounds of the device, chunks of at least 8 columns (the x-halo
-// costs 1/Mx extra reads and one extra y phase per chunk).
+// element columns (the x-halo costs 1/Mx extra reads and one extra y phase per chunk).
 inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_count, size_t smem_bytes, size_t smem_sm) {
     MarchGeom q;
     const March3Shape s = march3_shape(mode);
@@ -693,10 +755,11 @@ inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_
     if (resident < 1) resident = 1;
     int Mx = Mx_req;
     if (Mx <= 0) {
+        // chunks of 16 element columns measured best at config 5 (9 resident rounds: 0.39 ms against 0.46 ms for 3 rounds of
+        // 49 columns); shorter chunks, down to 8, only when the mesh is too small to fill the device 4 times over
         const long long slots = (long long)sm_count * resident;
-        const int want = (int)((3 * slots + strips - 1) / strips);   // ~3 rounds
-        Mx = (g.nex + want - 1) / want;
-        if (Mx < 8) Mx = 8;
+        Mx = 16;
+        while (Mx > 8 && (long long)strips * ((g.nex + Mx - 1) / Mx) < 4 * slots) Mx -= 4;
     }
     if (Mx > g.nex) Mx = g.nex;
     q.Ty = EW;
