@@ -4,7 +4,6 @@
 #include "sem_comm.cuh"
 #include "sem_dispatch.h"
 #include "sem_march.cuh"
-#include "sem_march2.cuh"
 #include "sem_march3.cuh"
 #include <cstdlib>
 
@@ -25,13 +24,11 @@ typedef int (*march_fn)(int, const MeshDev&, const MarchArgs&, const MarchGeom&,
 typedef size_t (*smem_fn)(int, int);
 typedef int (*upload_fn)(const double*, const double*, const double*);
 
-#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P, march2_launch_p##P, march2_smem_p##P, march3_launch_p##P, upload_tab3_p##P, march3_smem_p##P},
+#define SEM_TAB_ENTRY(P) {march_launch_p##P, march_smem_p##P, upload_tab_p##P, march3_launch_p##P, upload_tab3_p##P, march3_smem_p##P},
 static const struct {
     march_fn launch;
     smem_fn smem;
     upload_fn upload;
-    march_fn launch2;
-    smem_fn smem2;
     march_fn launch3;
     upload_fn upload3;
     size_t (*smem3)(int);
@@ -203,12 +200,12 @@ extern "C" int sem_d2h(sem_ctx* c, const double* vec, double* host, void* stream
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Kernel generation: v3 (TMA-staged, folded tables) for even orders; v1 for odd orders.  SEM_B200_MARCH=1 / 2 force the
-// older generations (A/B comparisons only).
+// Kernel generation: v3 (one warp per strip, TMA-staged, folded tables) for even orders; v1 for odd orders.
+// SEM_B200_MARCH=1 forces v1 everywhere (A/B comparisons only).
 static int march_generation() {
     static const int v = [] {
         const char* e = std::getenv("SEM_B200_MARCH");
-        return (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+        return (e && e[0] == '1') ? 1 : 3;
     }();
     return v;
 }
@@ -220,12 +217,6 @@ static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
     if (gen == 3 && c->g.P % 2 == 0) {
         const MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm);
         return ord.launch3(mode, c->g, A, q, st);
-    }
-    if (gen == 2 && ord.smem2(mode, 32) != 0) {
-        MarchGeom q = march2_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
-        while (ord.smem2(mode, q.pitch) > (size_t)c->smem_optin && q.Ty > 1)
-            q = march2_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count);
-        return ord.launch2(mode, c->g, A, q, st);
     }
     MarchGeom q = march_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
     // shrink the strip until the tile fits the opt-in shared memory of the device

@@ -10,8 +10,6 @@ struct MarchGeom;
 #define SEM_DECL_P(P)                                                                                         \
     int march_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
     size_t march_smem_p##P(int mode, int pitch);                                                               \
-    int march2_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
-    size_t march2_smem_p##P(int mode, int pitch);                                                              \
     int march3_launch_p##P(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st); \
     size_t march3_smem_p##P(int mode);                                                                         \
     int upload_tab3_p##P(const double* D, const double* Ks, const double* w);                                  \

@@ -1,7 +1,6 @@
 // One translation unit per polynomial order: compiled with -DSEM_P=<P> (see Makefile), so the 16 orders build in
 // parallel.  Exposes a launcher and a table uploader for that order through the registry in sem_dispatch.h.
 #include "sem_march.cuh"
-#include "sem_march2.cuh"
 #include "sem_march3.cuh"
 #include <cmath>
 #include "sem_dispatch.h"
@@ -40,36 +39,6 @@ int SEM_CAT(march_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& 
     }
     set_error("march_launch: unknown mode");
     return -2;
-}
-
-#if SEM_P % 2 == 0
-template <int P, int MODE>
-static int launch_mode2(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
-    const size_t smem = march2_smem_bytes<P, MODE>(q.pitch);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SEM_CUDA(cudaFuncSetAttribute(sem_march2_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
-        configured = smem;
-    }
-    sem_march2_kernel<P, MODE><<<q.grid, q.threads, smem, st>>>(g, A, q.Ty, q.Mx, q.pitch);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
-}
-#endif
-
-// v2 kernel (TMA-staged, two columns per thread): even orders, modes K / G / CD / DIV.  Returns 1 when not available.
-int SEM_CAT(march2_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q,
-                                    cudaStream_t st) {
-#if SEM_P % 2 == 0
-    switch (mode) {
-        case MODE_K: return launch_mode2<SEM_P, MODE_K>(g, A, q, st);
-        case MODE_G: return launch_mode2<SEM_P, MODE_G>(g, A, q, st);
-        case MODE_CD: return launch_mode2<SEM_P, MODE_CD>(g, A, q, st);
-        case MODE_DIV: return launch_mode2<SEM_P, MODE_DIV>(g, A, q, st);
-    }
-#endif
-    return 1;
 }
 
 // ---- v3 kernel (one warp per strip, TMA-staged, folded tables): even orders, all modes.  Returns 1 when not available.
@@ -157,18 +126,6 @@ int SEM_CAT(upload_tab3_p, SEM_P)(const double* D, const double* Ks, const doubl
     SEM_CUDA(cudaMemcpyToSymbol(c_tab3<P>, &h, sizeof(h)));
 #endif
     return 0;
-}
-
-size_t SEM_CAT(march2_smem_p, SEM_P)(int mode, int pitch) {
-#if SEM_P % 2 == 0
-    switch (mode) {
-        case MODE_K: return march2_smem_bytes<SEM_P, MODE_K>(pitch);
-        case MODE_G: return march2_smem_bytes<SEM_P, MODE_G>(pitch);
-        case MODE_CD: return march2_smem_bytes<SEM_P, MODE_CD>(pitch);
-        case MODE_DIV: return march2_smem_bytes<SEM_P, MODE_DIV>(pitch);
-    }
-#endif
-    return 0;   // 0 = this (order, mode) has no v2 kernel
 }
 
 size_t SEM_CAT(march_smem_p, SEM_P)(int mode, int pitch) {

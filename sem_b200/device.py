@@ -7,6 +7,7 @@ node line starts 128-byte aligned.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -21,6 +22,32 @@ def default_device():
         if os.environ.get(key, "") != "":
             return int(os.environ[key])
     return 0
+
+
+# Page-locked result arrays.  Every call hands out a FRESH numpy array (the reference returns fresh arrays too), backed by
+# a pinned block so that the D2H copy runs at the full link rate (54 GB/s measured against 21 GB/s into pageable memory);
+# a weakref finaliser puts the block back into a small pool once the array and all its views are gone, because
+# cudaHostAlloc of a large block costs ~130 ms.
+_PINNED_POOL = {}
+_PINNED_KEEP = 4
+
+
+def _pinned_release(n, block):
+    pool = _PINNED_POOL.setdefault(n, [])
+    if len(pool) < _PINNED_KEEP:
+        pool.append(block)
+
+
+def _pinned_result(n):
+    pool = _PINNED_POOL.get(n)
+    block = pool.pop() if pool else _alloc_pinned(n)
+    arr = block.numpy()                  # views of `arr` have `.base is arr`: it dies only after all of them
+    weakref.finalize(arr, _pinned_release, n, block)
+    return arr
+
+
+def _alloc_pinned(n):
+    return torch.empty(n, dtype=torch.float64).pin_memory()
 
 
 class SemDevice:
@@ -112,7 +139,7 @@ class SemDevice:
     def to_host(self, vec, out=None):
         """padded device vector -> fresh numpy (N,) (synchronises)."""
         if out is None:
-            out = np.empty(self.N_local, dtype=np.float64)
+            out = _pinned_result(self.N_local)
         L.check(self.lib.sem_d2h(self.ctx, vec.data_ptr(), out.ctypes.data, self.stream), "sem_d2h")
         return out
 

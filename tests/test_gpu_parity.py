@@ -77,6 +77,45 @@ def test_all_orders_and_tilings_against_oracle(sem, P, tiling):
     assert relerr(d.to_host(y2), 2.5 * (Gy @ xh)) < APPLY_TOL
 
 
+@pytest.mark.parametrize("P", [2, 4, 6, 8, 10, 12, 14, 16])
+@pytest.mark.parametrize("extra_rows", [0, 1])
+def test_warp_strips_even_orders(sem, P, extra_rows):
+    """v3 kernel (even orders): one warp owns EW = 64/P element rows (32/P for NS).  Meshes of 2*EW (+1) rows force the
+    y-halo path, a last strip that holds one element row or none (only the topmost node column), and -- with chunks of one
+    and two element columns -- the x-halo path; all five modes against the oracle's CSR operators."""
+    from oracle import sem_oracle as so
+    EW = 64 // P
+    nx, ny, Lx, Ly = 3, 2 * EW + extra_rows, 0.7, 1.9
+    rng = np.random.default_rng(P * 10 + extra_rows)
+    cd_o = so.CDOracle(Lx, Ly, 7.0, P, nx, ny, T_W=0.5, T_E=-0.5, T_S=0.25)
+    ns_o = so.NSOracle(Lx, Ly, 30.0, 5.0, P, nx, ny, u_N=1.0, v_W=0.3)
+    N = cd_o.N
+    T, u, v, p, dT, du, dv, dp = (rng.standard_normal(N) for _ in range(8))
+    M, K, Gx, Gy = so.global_operators(P, nx, ny, Lx / nx, Ly / ny)
+    cd = sem.ConvectionDiffusionSolver(Lx, Ly, 7.0, P, nx, ny, T_W=0.5, T_E=-0.5, T_S=0.25)
+    ns = sem.NavierStokesSolver(Lx, Ly, 30.0, 5.0, P, nx, ny, u_N=1.0, v_W=0.3, iprint=[])
+    d = cd._dev
+    for Mx in (0, 1, 2):
+        d.set_tiling(0, Mx)
+        ns._dev.set_tiling(0, Mx)
+        x = d.to_device(T)
+        y, y2 = d.zeros(), d.zeros()
+        assert relerr(d.to_host(d.apply_stiffness(x, y)), K @ T) < APPLY_TOL
+        d.apply_gradient(x, y, y2, scale=1.5)
+        assert relerr(d.to_host(y), 1.5 * (Gx @ T)) < APPLY_TOL and relerr(d.to_host(y2), 1.5 * (Gy @ T)) < APPLY_TOL
+        assert relerr(cd._get_residuals(T, u, v), cd_o._get_residuals(T, u, v)) < APPLY_TOL
+        cd._calc_jacobians(T), cd_o._calc_jacobians(T)
+        assert relerr(cd._get_dresiduals(dT), cd_o._get_dresiduals(dT)) < APPLY_TOL
+        assert relerr(cd._get_dresiduals(dT, du, dv), cd_o._get_dresiduals(dT, du, dv)) < APPLY_TOL
+        for a, b in zip(ns._get_residuals(u, v, p, T), ns_o._get_residuals(u, v, p, T)):
+            assert relerr(a, b) < APPLY_TOL
+        ns._calc_jacobians(u, v), ns_o._calc_jacobians(u, v)
+        for a, b in zip(ns._get_dresiduals(du, dv, dp), ns_o._get_dresiduals(du, dv, dp)):
+            assert relerr(a, b) < APPLY_TOL
+        for a, b in zip(ns._get_dresiduals(du, dv, dp, dT), ns_o._get_dresiduals(du, dv, dp, dT)):
+            assert relerr(a, b) < APPLY_TOL
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("tag,kw", CD_CASES)
 def test_cd_matches_reference(sem, golden, tag, kw):

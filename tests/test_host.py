@@ -73,3 +73,27 @@ def test_host_mesh_functions_match_reference(golden, tag, P, nx, ny, Lx, Ly):
         SEM.xi2x(0, np.array([1.5]), 1.0)
     e, xi = SEM.x2xi(np.array([0.0, Lx / nx, Lx]), Lx / nx)
     assert list(e) == [0, 0, nx - 1] and np.allclose(xi, [-1, 1, 1])
+
+
+def test_pinned_result_pool_recycles_only_dead_arrays(monkeypatch):
+    """Result arrays are fresh per call; their page-locked block returns to the pool only after the array AND all of its
+    views are gone (sem_b200/device.py)."""
+    import gc
+    import torch
+    import sem_b200.device as D
+    monkeypatch.setattr(D, "_alloc_pinned", lambda n: torch.empty(n, dtype=torch.float64))   # no CUDA on the CPU box
+    monkeypatch.setattr(D, "_PINNED_POOL", {})
+    a = D._pinned_result(12)
+    a[:] = 3.0
+    view = a[2:5].reshape(3, 1)
+    b = D._pinned_result(12)
+    assert not np.shares_memory(a, b)
+    del a
+    gc.collect()
+    assert D._PINNED_POOL.get(12, []) == []          # the view keeps the block out of the pool
+    assert float(view[0, 0]) == 3.0
+    del view
+    gc.collect()
+    assert len(D._PINNED_POOL[12]) == 1
+    c = D._pinned_result(12)                         # recycled block
+    assert D._PINNED_POOL[12] == [] and c.shape == (12,)
