@@ -116,6 +116,14 @@ int sem_cd_residual(sem_ctx *ctx, const sem_cd_state *st, const double *T, doubl
 int sem_cd_jacobians(sem_ctx *ctx, double Pe, const double *T, double *gxT, double *gyT, void *stream);
 int sem_cd_jvp(sem_ctx *ctx, const sem_cd_state *st, const double *dT, const double *du, const double *dv,
                double *dres, void *stream);
+/* The same product with HOST vectors (the reference's call: numpy in, numpy out, CD:104-121 with du = dv = None):
+ * host_dT and host_dres are dense local vectors of NX_local*NY doubles (page-locked memory gives the full link rate).
+ * The element columns are processed in segments: the upload of segment s+1, the kernel of segment s and the download of
+ * segment s-1 run concurrently (PCIe is full duplex), so the call costs about one direction of the transfer instead of
+ * upload + kernel + download.  dT_vec / dres_vec: device vecs that receive the padded input / output (scratch of the
+ * caller).  Returns after the result is complete in host_dres.  Not available on a partitioned context. */
+int sem_cd_jvp_host(sem_ctx *ctx, const sem_cd_state *st, const double *host_dT, double *host_dres,
+                    double *dT_vec, double *dres_vec, void *stream);
 /* CD._get_update (CD:123-156): solve J dT = rhs; dT holds the initial guess on entry. work >= sem_cd_work_len(). */
 long long sem_cd_work_len(const sem_ctx *ctx, int restart);
 int sem_cd_solve(sem_ctx *ctx, const sem_cd_state *st, const double *rhs, double *dT, sem_krylov *kr,

@@ -139,6 +139,14 @@ class ConvectionDiffusionSolver:
             raise RuntimeError('ConvectionDiffusion: _get_residuals must be called before _get_dresiduals')
         if (du is not None or dv is not None) and not self._have_jac:
             raise RuntimeError('ConvectionDiffusion: _calc_jacobians must be called before passing du/dv')
+        if du is None and dv is None and d.part is None:
+            # host vector in, host vector out: upload, apply and download pipelined over segments of element columns
+            a, out = d._host(dT), d.host_result()
+            st = self._state(with_jac=False)
+            L.check(self._lib.sem_cd_jvp_host(d.ctx, C.byref(st), a.ctypes.data, out.ctypes.data,
+                                              self._buf[0].data_ptr(), self._buf[1].data_ptr(), d.stream),
+                    "sem_cd_jvp_host")
+            return out
         dTd = d.to_device(dT, self._buf[0])
         dud = d.to_device(du, self._buf[2]) if du is not None else None
         dvd = d.to_device(dv, self._buf[3]) if dv is not None else None

@@ -136,29 +136,40 @@ int aux_neumann_rows(const MeshDev& g, TabDev t, const double* c, double* y, int
 
 // ---------------------------------------------------------------------------------------------------------------
 // dense <-> padded repacking
-// ---------------------------------------------------------------------------------------------------------------
+// --------------------------------------------------------------------------------------------
 template <bool PAD>
-__global__ void k_repack(const MeshDev g, const double* __restrict__ src, double* __restrict__ dst) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tot = (long long)g.NX * g.NY;
-    if (idx >= tot) return;
+__global__ void k_repack(const MeshDev g, const double* __restrict__ src, double* __restrict__ dst, long long first,
+                         long long count) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const long long idx = first + k;
     const long long ix = idx / g.NY, iy = idx % g.NY;
     if (PAD) dst[ix * g.LD + iy] = src[idx];
     else dst[idx] = src[ix * g.LD + iy];
 }
 
-int aux_pad(const MeshDev& g, const double* dense, double* vec, cudaStream_t st) {
-    const long long tot = (long long)g.NX * g.NY;
-    k_repack<true><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, dense, vec);
+int aux_pad_lines(const MeshDev& g, const double* dense, double* vec, int line0, int nlines, cudaStream_t st) {
+    const long long count = (long long)nlines * g.NY;
+    if (count <= 0) return 0;
+    k_repack<true><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(g, dense, vec, (long long)line0 * g.NY, count);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }
 
-int aux_unpad(const MeshDev& g, const double* vec, double* dense, cudaStream_t st) {
-    const long long tot = (long long)g.NX * g.NY;
-    k_repack<false><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, vec, dense);
+int aux_unpad_lines(const MeshDev& g, const double* vec, double* dense, int line0, int nlines, cudaStream_t st) {
+    const long long count = (long long)nlines * g.NY;
+    if (count <= 0) return 0;
+    k_repack<false><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(g, vec, dense, (long long)line0 * g.NY, count);
     SEM_CUDA(cudaGetLastError());
     return 0;
+}
+
+int aux_pad(const MeshDev& g, const double* dense, double* vec, cudaStream_t st) {
+    return aux_pad_lines(g, dense, vec, 0, g.NX, st);
+}
+
+int aux_unpad(const MeshDev& g, const double* vec, double* dense, cudaStream_t st) {
+    return aux_unpad_lines(g, vec, dense, 0, g.NX, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

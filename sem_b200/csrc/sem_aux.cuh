@@ -24,6 +24,9 @@ int aux_neumann_rows(const MeshDev& g, TabDev t, const double* c, double* y, int
 // dense [NX][NY] <-> padded [NX][LD] repacking on the device (host copies stay 1-D and run at full PCIe rate)
 int aux_pad(const MeshDev& g, const double* dense, double* vec, cudaStream_t st);
 int aux_unpad(const MeshDev& g, const double* vec, double* dense, cudaStream_t st);
+// the same for node lines line0 .. line0 + nlines - 1 only (`dense` and `vec` still point to line 0)
+int aux_pad_lines(const MeshDev& g, const double* dense, double* vec, int line0, int nlines, cudaStream_t st);
+int aux_unpad_lines(const MeshDev& g, const double* vec, double* dense, int line0, int nlines, cudaStream_t st);
 
 // SEM.assemble (4-index) / SEM.scatter, element array [m][n][i][j]
 int aux_gather_scatter(const MeshDev& g, const double* elem, double* y, cudaStream_t st);

@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -34,6 +35,8 @@ static const struct {
     size_t (*smem3)(int);
 } g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
 
+#define SEM_HOST_SEGMENTS 8   // element-column segments of the host-buffer pipeline
+
 struct sem_ctx {
     MeshDev g;
     int device, sm_count, smem_optin, smem_sm;
@@ -48,6 +51,13 @@ struct sem_ctx {
     int small_len;
     Comm comm;               // NCCL communicator of the element-column partition (has_comm)
     int has_comm;
+    cudaStream_t s_side;     // low-priority stream: the interior of an operator runs here while the interface lines travel
+    cudaEvent_t ev_in, ev_side;
+    // host-buffer pipeline (sem_cd_jvp_host): upload / download streams, second staging buffer, per-segment events
+    cudaStream_t s_h2d, s_d2h;
+    double* dStageOut;
+    cudaEvent_t ev_up[SEM_HOST_SEGMENTS], ev_done[SEM_HOST_SEGMENTS], ev_start, ev_end;
+    int streams_ready;
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
 };
 
@@ -125,6 +135,12 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     if (c->dKdiag) cudaFree(c->dKdiag);
     if (c->dStage) cudaFree(c->dStage);
     if (c->has_comm) comm_destroy(c->comm);
+    if (c->dStageOut) cudaFree(c->dStageOut);
+    if (c->streams_ready) {
+        cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
+        cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
+        for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
+    }
     cudaFree(c->rs.partials); cudaFree(c->rs.counter);
     cudaFree(c->d_small); cudaFreeHost(c->h_small);
     delete c;
@@ -210,20 +226,82 @@ static int march_generation() {
     return v;
 }
 
-static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
+// one fused operator launch over the element columns [m_lo, m_hi) of the slab (m_hi < 0: all)
+static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st, int m_lo = 0, int m_hi = -1) {
     A.zero = 0;
+    if (m_hi < 0) m_hi = c->g.nex;
+    if (m_lo >= m_hi) return 0;
     const auto& ord = g_orders[c->g.P - 1];
     const int gen = march_generation();
     if (gen == 3 && c->g.P % 2 == 0) {
-        const MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm);
+        const MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm, m_lo, m_hi);
         return ord.launch3(mode, c->g, A, q, st);
     }
-    MarchGeom q = march_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count);
+    MarchGeom q = march_geometry(c->g, c->Ty_req, c->Mx_req, c->sm_count, m_lo, m_hi);
     // shrink the strip until the tile fits the opt-in shared memory of the device
     while (g_orders[c->g.P - 1].smem(mode, q.pitch) > (size_t)c->smem_optin && q.Ty > 1) {
-        q = march_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count);
+        q = march_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count, m_lo, m_hi);
     }
     return g_orders[c->g.P - 1].launch(mode, c->g, A, q, st);
+}
+
+static int ensure_streams(sem_ctx* c) {
+    if (c->streams_ready) return 0;
+    int lo = 0, hi = 0;
+    SEM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority
+    SEM_CUDA(cudaStreamCreateWithPriority(&c->s_side, cudaStreamNonBlocking, lo));
+    SEM_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    SEM_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_end, cudaEventDisableTiming));
+    for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) {
+        SEM_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+        SEM_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    c->streams_ready = 1;
+    return 0;
+}
+
+// A fused operator apply followed by the interface exchange of its outputs (`fields`; null entries are skipped).
+// `post` (optional) runs after the operator and before the exchange (the O(sqrt N) pressure-Neumann rows of NS).
+// One GPU: operator, post.  Partitioned: the element columns next to the interfaces are applied first, their interface
+// lines travel (NCCL send/recv on the caller's stream) while the interior columns are applied on a low-priority side
+// stream, then the received partial sums are added.  `post` is idempotent and cheap, so it simply runs before the
+// transfer (interface lines final) and again after the interior (interior lines final).
+static const int SEM_EDGE_COLUMNS = 16;
+
+static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializer_list<double*> fields, cudaStream_t st,
+                              const std::function<int()>& post = nullptr) {
+    if (!c->has_comm) {
+        if (march(c, mode, A, st)) return -1;
+        return post ? post() : 0;
+    }
+    double* f[8];
+    int n = 0;
+    for (double* p : fields)
+        if (p) f[n++] = p;
+    const int nex = c->g.nex;
+    const int el = c->g.has_left ? std::min(SEM_EDGE_COLUMNS, nex) : 0;
+    const int er = c->g.has_right ? std::min(SEM_EDGE_COLUMNS, nex - el) : 0;
+    if (el + er >= nex || n == 0) {   // nothing left to overlap with
+        if (march(c, mode, A, st)) return -1;
+        if (post && post()) return -1;
+        return n ? comm_exchange_add(c->comm, c->g, f, n, st) : 0;
+    }
+    if (ensure_streams(c)) return -1;
+    SEM_CUDA(cudaEventRecord(c->ev_in, st));                 // inputs are ready here
+    if (march(c, mode, A, st, 0, el)) return -1;
+    if (march(c, mode, A, st, nex - er, nex)) return -1;
+    if (post && post()) return -1;
+    SEM_CUDA(cudaStreamWaitEvent(c->s_side, c->ev_in, 0));
+    if (march(c, mode, A, c->s_side, el, nex - er)) return -1;
+    SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
+    if (comm_exchange_transfer(c->comm, c->g, f, n, st)) return -1;
+    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
+    if (post && post()) return -1;
+    return comm_exchange_finish(c->comm, c->g, f, n, st);
 }
 
 static MarchArgs zero_args() {
@@ -263,8 +341,7 @@ extern "C" int sem_apply_stiffness(sem_ctx* c, const double* x, double* y, void*
     MarchArgs A = zero_args();
     A.a = x;
     A.y0 = y;
-    if (march(c, MODE_K, A, (cudaStream_t)stream)) return -1;
-    return exchange(c, {y}, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_K, A, {y}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_apply_gradient(sem_ctx* c, const double* x, double scale, double* gx, double* gy, void* stream) {
@@ -274,8 +351,7 @@ extern "C" int sem_apply_gradient(sem_ctx* c, const double* x, double scale, dou
     A.y0 = gx;
     A.y1 = gy;
     A.cconv = scale;
-    if (march(c, MODE_G, A, (cudaStream_t)stream)) return -1;
-    return exchange(c, {gx, gy}, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_G, A, {gx, gy}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_apply_mass(sem_ctx* c, const double* x, double* y, void* stream) {
@@ -307,8 +383,7 @@ extern "C" int sem_cd_residual(sem_ctx* c, const sem_cd_state* s, const double* 
     MarchArgs A = zero_args();
     A.a = T; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = res;
     fill_cd_bc(A.bc, s->bc, 1);
-    if (march(c, MODE_CD, A, (cudaStream_t)stream)) return -1;
-    return exchange(c, {res}, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_CD, A, {res}, (cudaStream_t)stream);
 }
 
 extern "C" int sem_cd_jacobians(sem_ctx* c, double Pe, const double* T, double* gxT, double* gyT, void* stream) {
@@ -323,8 +398,55 @@ extern "C" int sem_cd_jvp(sem_ctx* c, const sem_cd_state* s, const double* dT, c
     A.a = dT; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = dres;
     A.d0 = s->gxT; A.e0 = du; A.d1 = s->gyT; A.e1 = dv;
     fill_cd_bc(A.bc, s->bc, 0);
-    if (march(c, MODE_CD, A, (cudaStream_t)stream)) return -1;
-    return exchange(c, {dres}, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_CD, A, {dres}, (cudaStream_t)stream);
+}
+
+// Host-buffer variant of sem_cd_jvp: three streams, SEM_HOST_SEGMENTS segments of element columns.
+//   s_h2d : dense upload of the node lines of segment s            -> ev_up[s]
+//   stream: wait ev_up[s]; pad lines; fused apply of the segment's element columns; unpad the finished lines -> ev_done[s]
+//   s_d2h : wait ev_done[s]; dense download of the finished lines
+// A segment [ma, mb) reads the lines (ma-1)*P .. mb*P (the first P+1 of them were uploaded with the previous segment)
+// and finishes the lines ma*P .. mb*P-1, plus the last line of the slab when mb is the last column.
+extern "C" int sem_cd_jvp_host(sem_ctx* c, const sem_cd_state* s, const double* host_dT, double* host_dres,
+                               double* dT_vec, double* dres_vec, void* stream) {
+    SEM_CHECK_CTX(c);
+    if (c->has_comm) { set_error("sem_cd_jvp_host: not available on a partitioned context"); return -2; }
+    const MeshDev& g = c->g;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ensure_stage(c) || ensure_streams(c)) return -1;
+    if (!c->dStageOut) SEM_CUDA(cudaMalloc(&c->dStageOut, sizeof(double) * (size_t)g.NX * g.NY));
+    MarchArgs A = zero_args();
+    A.a = dT_vec; A.U = s->u; A.V = s->v; A.cconv = s->Pe; A.y0 = dres_vec;
+    fill_cd_bc(A.bc, s->bc, 0);
+    // segments of whole 16-column chunks (the chunk size of the kernel), at most SEM_HOST_SEGMENTS
+    const int chunk = 16;
+    const int nchunks = (g.nex + chunk - 1) / chunk;
+    const int nseg = std::max(1, std::min(SEM_HOST_SEGMENTS, nchunks));
+    SEM_CUDA(cudaEventRecord(c->ev_start, st));              // earlier work on the caller's stream (state vectors ...)
+    SEM_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_start, 0));
+    SEM_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_start, 0));
+    const size_t NY = (size_t)g.NY;
+    for (int k = 0; k < nseg; ++k) {
+        const int ma = (int)((long long)nchunks * k / nseg) * chunk;
+        const int mb = std::min(g.nex, (int)((long long)nchunks * (k + 1) / nseg) * chunk);
+        const int up0 = (k == 0) ? 0 : ma * g.P + 1, up1 = mb * g.P;                  // lines uploaded for this segment
+        const int dn0 = ma * g.P, dn1 = (mb == g.nex) ? g.nex * g.P : mb * g.P - 1;   // lines this segment finishes
+        SEM_CUDA(cudaMemcpyAsync(c->dStage + (size_t)up0 * NY, host_dT + (size_t)up0 * NY, sizeof(double) * (up1 - up0 + 1) * NY,
+                                 cudaMemcpyHostToDevice, c->s_h2d));
+        SEM_CUDA(cudaEventRecord(c->ev_up[k], c->s_h2d));
+        SEM_CUDA(cudaStreamWaitEvent(st, c->ev_up[k], 0));
+        if (aux_pad_lines(g, c->dStage, dT_vec, up0, up1 - up0 + 1, st)) return -1;
+        if (march(c, MODE_CD, A, st, ma, mb)) return -1;
+        if (aux_unpad_lines(g, dres_vec, c->dStageOut, dn0, dn1 - dn0 + 1, st)) return -1;
+        SEM_CUDA(cudaEventRecord(c->ev_done[k], st));
+        SEM_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_done[k], 0));
+        SEM_CUDA(cudaMemcpyAsync(host_dres + (size_t)dn0 * NY, c->dStageOut + (size_t)dn0 * NY,
+                                 sizeof(double) * (dn1 - dn0 + 1) * NY, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    SEM_CUDA(cudaEventRecord(c->ev_end, c->s_d2h));
+    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_end, 0));         // the caller's stream stays the single point of ordering
+    SEM_CUDA(cudaStreamSynchronize(st));
+    return 0;
 }
 
 // ---- Navier-Stokes ------------------------------------------------------------------------------------------------
@@ -336,11 +458,10 @@ extern "C" int sem_ns_residual(sem_ctx* c, const sem_ns_state* s, const double* 
     A.e0 = T; A.cbuoy = -s->Gr_over_Re;
     A.y0 = ru; A.y1 = rv; A.y2 = rc;
     fill_ns_bc(c, A.bc, s->bc, 1);
-    int rcode = march(c, MODE_NS, A, (cudaStream_t)stream);
-    if (rcode) return rcode;
     // NS:116-119: pin first, then the Neumann rows (they win if the pin sits on the boundary)
-    if (aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, (cudaStream_t)stream)) return -1;
-    return exchange(c, {ru, rv, rc}, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_NS, A, {ru, rv, rc}, (cudaStream_t)stream, [&]() {
+        return aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, (cudaStream_t)stream);
+    });
 }
 
 extern "C" int sem_ns_jacobians(sem_ctx* c, double Re, const double* u, const double* v, double* gxu, double* gyu,
@@ -360,11 +481,10 @@ extern "C" int sem_ns_jvp(sem_ctx* c, const sem_ns_state* s, const double* du, c
     A.e0 = dT; A.cbuoy = -s->Gr_over_Re;
     A.y0 = ou; A.y1 = ov; A.y2 = oc;
     fill_ns_bc(c, A.bc, s->bc, 0);
-    int rcode = march(c, MODE_NS, A, (cudaStream_t)stream);
-    if (rcode) return rcode;
     // NS:157-158: Neumann rows first, then the pin (the pin wins)
-    if (aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, (cudaStream_t)stream)) return -1;
-    return exchange(c, {ou, ov, oc}, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_NS, A, {ou, ov, oc}, (cudaStream_t)stream, [&]() {
+        return aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, (cudaStream_t)stream);
+    });
 }
 
 // ---- reductions ------------------------------------------------------------------------------------------------------
@@ -558,8 +678,7 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
         if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) return -1;
         MarchArgs A = zero_args();
         A.a = z; A.b = z + vlen; A.y0 = tmp;
-        if (march(c, MODE_DIV, A, st)) return -1;
-        if (exchange(c, {tmp}, st)) return -1;
+        if (apply_and_exchange(c, MODE_DIV, A, {tmp}, st)) return -1;
         return aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st);
     };
     GmresLayout L{n, 3, vlen};

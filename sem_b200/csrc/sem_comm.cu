@@ -110,36 +110,48 @@ __global__ void k_halo_add(const LinePtrs p, int NY) {
     p.line[q][iy] = p.lower_first[q] ? (mine + other) : (other + mine);
 }
 
-int comm_exchange_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
-    if (nf > c.max_fields) { set_error("comm_exchange_add: too many fields"); return -2; }
+int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
     if (!g.has_left && !g.has_right) return 0;
     ncclComm_t comm = (ncclComm_t)c.nccl;
     const size_t NY = (size_t)g.NY;
     const size_t last = (size_t)(g.NX - 1) * g.LD;
-    LinePtrs lp;
-    lp.n = 0;
     SEM_NCCL(g_nccl.GroupStart());
     for (int f = 0; f < nf; ++f) {
         if (g.has_left) {
-            double* rbuf = c.recv + (size_t)(0 * c.max_fields + f) * NY;
             SEM_NCCL(g_nccl.Send(fields[f], NY, ncclDouble, c.rank - 1, comm, st));
-            SEM_NCCL(g_nccl.Recv(rbuf, NY, ncclDouble, c.rank - 1, comm, st));
+            SEM_NCCL(g_nccl.Recv(c.recv + (size_t)(0 * c.max_fields + f) * NY, NY, ncclDouble, c.rank - 1, comm, st));
+        }
+        if (g.has_right) {
+            SEM_NCCL(g_nccl.Send(fields[f] + last, NY, ncclDouble, c.rank + 1, comm, st));
+            SEM_NCCL(g_nccl.Recv(c.recv + (size_t)(1 * c.max_fields + f) * NY, NY, ncclDouble, c.rank + 1, comm, st));
+        }
+    }
+    SEM_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+int comm_exchange_finish(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
+    if (!g.has_left && !g.has_right) return 0;
+    const size_t NY = (size_t)g.NY;
+    const size_t last = (size_t)(g.NX - 1) * g.LD;
+    LinePtrs lp;
+    lp.n = 0;
+    for (int f = 0; f < nf; ++f) {
+        if (g.has_left) {
             lp.line[lp.n] = fields[f];
-            lp.recv[lp.n] = rbuf;
+            lp.recv[lp.n] = c.recv + (size_t)(0 * c.max_fields + f) * NY;
             lp.lower_first[lp.n] = 0;   // the neighbour is the lower rank: its partial goes first
             lp.n++;
         }
         if (g.has_right) {
-            double* rbuf = c.recv + (size_t)(1 * c.max_fields + f) * NY;
-            SEM_NCCL(g_nccl.Send(fields[f] + last, NY, ncclDouble, c.rank + 1, comm, st));
-            SEM_NCCL(g_nccl.Recv(rbuf, NY, ncclDouble, c.rank + 1, comm, st));
             lp.line[lp.n] = fields[f] + last;
-            lp.recv[lp.n] = rbuf;
+            lp.recv[lp.n] = c.recv + (size_t)(1 * c.max_fields + f) * NY;
             lp.lower_first[lp.n] = 1;
             lp.n++;
         }
     }
-    SEM_NCCL(g_nccl.GroupEnd());
     dim3 grid((unsigned)((g.NY + 255) / 256), (unsigned)lp.n);
     k_halo_add<<<grid, 256, 0, st>>>(lp, g.NY);
     SEM_CUDA(cudaGetLastError());

@@ -20,6 +20,14 @@ void comm_destroy(Comm& c);
 int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st);
 // Interface exchange after a local operator apply: every field's interface line(s) hold this rank's element sums;
 // send them to the neighbour(s), receive theirs and add (two-term sum: bitwise identical on both ranks).
-int comm_exchange_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st);
+// Two halves so that the caller can run the interior of the operator between them (on another stream):
+//   comm_exchange_transfer: ncclSend/ncclRecv of the interface lines into the receive staging;
+//   comm_exchange_finish:   line = own + received (lower rank's term first).
+int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st);
+int comm_exchange_finish(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st);
+inline int comm_exchange_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    if (comm_exchange_transfer(c, g, fields, nf, st)) return -1;
+    return comm_exchange_finish(c, g, fields, nf, st);
+}
 
 }  // namespace semb

@@ -368,7 +368,7 @@ struct March {
 
 template <int P, int MODE>
 __global__ void __launch_bounds__(SEM_MARCH_MAXT, ModeTraits<MODE>::MINB) sem_march_kernel(const MeshDev g, const MarchArgs A, const int Ty,
-                                                         const int Mx, const int pitch) {
+                                                         const int Mx, const int pitch, const int m_lo, const int m_hi) {
     using MM = March<P, MODE>;
     constexpr int n = P + 1;
     constexpr int NF = MM::NF, NV = MM::NV, NACC = MM::NACC, NOUT = MM::NOUT;
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(SEM_MARCH_MAXT, ModeTraits<MODE>::MINB) sem_ma
 
     const int n0 = blockIdx.x * Ty;
     const int nty = min(Ty, g.ney - n0);
-    const int m0 = blockIdx.y * Mx;
-    const int m1 = min(m0 + Mx, g.nex);
+    const int m0 = m_lo + blockIdx.y * Mx;   // the launch covers the element columns m_lo .. m_hi - 1
+    const int m1 = min(m0 + Mx, m_hi);
     const int halo = (n0 > 0) ? P : 0;
     const int ybase = n0 * P - halo;
     const int ncol = halo + nty * P + 1;
@@ -474,11 +474,11 @@ __global__ void __launch_bounds__(SEM_MARCH_MAXT, ModeTraits<MODE>::MINB) sem_ma
 // Host-side launch geometry shared by all instantiations.
 struct MarchGeom {
     int Ty, Mx, pitch, threads;
-    int tp = 0;   // pitch of the top-row side array (v3 kernel only)
+    int m_lo = 0, m_hi = 0;   // element columns covered by the launch
     dim3 grid;
 };
 
-inline MarchGeom march_geometry(const MeshDev& g, int Ty_req, int Mx_req, int sm_count) {
+inline MarchGeom march_geometry(const MeshDev& g, int Ty_req, int Mx_req, int sm_count, int m_lo, int m_hi) {
     MarchGeom q;
     const int P = g.P;
     int Ty = Ty_req > 0 ? Ty_req : (256 / P > 0 ? 256 / P : 1);
@@ -499,7 +499,9 @@ inline MarchGeom march_geometry(const MeshDev& g, int Ty_req, int Mx_req, int sm
     const int ncol = P + Ty * P + 1;
     q.pitch = ncol + ((17 - ncol % 16) % 16);   // smallest pitch >= ncol with pitch % 16 == 1
     q.threads = round_up(ncol > Ty * P + P ? ncol : Ty * P + P, 32);
-    q.grid = dim3((unsigned)strips, (unsigned)((g.nex + Mx - 1) / Mx), 1);
+    q.m_lo = m_lo;
+    q.m_hi = m_hi;
+    q.grid = dim3((unsigned)strips, (unsigned)((m_hi - m_lo + Mx - 1) / Mx), 1);
     return q;
 }
 

@@ -532,7 +532,7 @@ struct March3 {
 
 template <int P, int MODE, bool PW>
 __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ MeshDev g, const __grid_constant__ MarchArgs A,
-                                                        const int Mx) {
+                                                        const int Mx, const int m_lo, const int m_hi) {
     using M3 = March3<P, MODE, PW>;
     using GE = March3Geom<P, MODE>;
     constexpr int NF = M3::NF, NACC = M3::NACC, NOUT = M3::NOUT, NSTG = M3::NSTG, NC = M3::NC, NL = M3::NL, G = M3::G;
@@ -548,8 +548,8 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     const int n0 = blockIdx.x * EW;
     const int nty = max(0, min(EW, g.ney - n0));          // the last strip holds the remaining ney % EW rows (maybe none)
     const bool last_strip = (blockIdx.x == gridDim.x - 1);
-    const int m0 = blockIdx.y * Mx;
-    const int m1 = min(m0 + Mx, g.nex);
+    const int m0 = m_lo + blockIdx.y * Mx;              // the launch covers the element columns m_lo .. m_hi - 1
+    const int m1 = min(m0 + Mx, m_hi);
     const int halo = (n0 > 0) ? P : 0;
     const int ybase = n0 * P - halo;                      // even
     const int ncolp = (halo + nty * P + 1 + 1) & ~1;      // staged columns per line (even)
@@ -745,7 +745,8 @@ inline March3Shape march3_shape(int mode) {
 
 // grid: x = strips of EW element rows (+ the last strip with the remainder and the topmost node column), y = chunks of Mx
 // element columns (the x-halo costs 1/Mx extra reads and one extra y phase per chunk).
-inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_count, size_t smem_bytes, size_t smem_sm) {
+inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_count, size_t smem_bytes, size_t smem_sm,
+                                 int m_lo, int m_hi) {
     MarchGeom q;
     const March3Shape s = march3_shape(mode);
     const int EW = (32 * s.nc / g.P) > 0 ? (32 * s.nc / g.P) : 1;
@@ -766,7 +767,9 @@ inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_
     q.Mx = Mx;
     q.pitch = 0;
     q.threads = 32;
-    q.grid = dim3((unsigned)strips, (unsigned)((g.nex + Mx - 1) / Mx), 1);
+    q.m_lo = m_lo;
+    q.m_hi = m_hi;
+    q.grid = dim3((unsigned)strips, (unsigned)((m_hi - m_lo + Mx - 1) / Mx), 1);
     return q;
 }
 

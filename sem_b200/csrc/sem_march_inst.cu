@@ -20,7 +20,7 @@ static int launch_mode(const MeshDev& g, const MarchArgs& A, const MarchGeom& q,
                                       (int)(smem > 48 * 1024 ? smem : 48 * 1024)));
         configured = smem;
     }
-    sem_march_kernel<P, MODE><<<q.grid, q.threads, smem, st>>>(g, A, q.Ty, q.Mx, q.pitch);
+    sem_march_kernel<P, MODE><<<q.grid, q.threads, smem, st>>>(g, A, q.Ty, q.Mx, q.pitch, q.m_lo, q.m_hi);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -52,7 +52,7 @@ static int launch_mode3(const MeshDev& g, const MarchArgs& A, const MarchGeom& q
             SEM_CUDA(cudaFuncSetAttribute(sem_march3_kernel<P, MODE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    sem_march3_kernel<P, MODE, PW><<<q.grid, 32, smem, st>>>(g, A, q.Mx);
+    sem_march3_kernel<P, MODE, PW><<<q.grid, 32, smem, st>>>(g, A, q.Mx, q.m_lo, q.m_hi);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }

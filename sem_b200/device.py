@@ -136,6 +136,10 @@ class SemDevice:
         torch.cuda.current_stream(self.tdev).synchronize()
         return out
 
+    def host_result(self):
+        """A fresh page-locked numpy vector of the local length (see ``_pinned_result``)."""
+        return _pinned_result(self.N_local)
+
     def to_host(self, vec, out=None):
         """padded device vector -> fresh numpy (N,) (synchronises)."""
         if out is None:
