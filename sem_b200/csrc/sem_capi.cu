@@ -52,7 +52,7 @@ struct sem_ctx {
     Comm comm;               // NCCL communicator of the element-column partition (has_comm)
     int has_comm;
     cudaStream_t s_side;     // low-priority stream: the interior of an operator runs here while the interface lines travel
-    cudaEvent_t ev_in, ev_side;
+    cudaEvent_t ev_in, ev_edge, ev_side;
     // host-buffer pipeline (sem_cd_jvp_host): upload / download streams, second staging buffer, per-segment events
     cudaStream_t s_h2d, s_d2h;
     double* dStageOut;
@@ -138,7 +138,7 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     if (c->dStageOut) cudaFree(c->dStageOut);
     if (c->streams_ready) {
         cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
-        cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
+        cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_edge); cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
         for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
     }
     cudaFree(c->rs.partials); cudaFree(c->rs.counter);
@@ -254,6 +254,7 @@ static int ensure_streams(sem_ctx* c) {
     SEM_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_end, cudaEventDisableTiming));
     for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) {
@@ -270,7 +271,7 @@ static int ensure_streams(sem_ctx* c) {
 // lines travel (NCCL send/recv on the caller's stream) while the interior columns are applied on a low-priority side
 // stream, then the received partial sums are added.  `post` is idempotent and cheap, so it simply runs before the
 // transfer (interface lines final) and again after the interior (interior lines final).
-static const int SEM_EDGE_COLUMNS = 16;
+static const int SEM_EDGE_COLUMNS = 4;   // a launch this narrow is pure latency (one warp per strip, 4 marching steps)
 
 static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializer_list<double*> fields, cudaStream_t st,
                               const std::function<int()>& post = nullptr) {
@@ -292,12 +293,14 @@ static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializ
     }
     if (ensure_streams(c)) return -1;
     SEM_CUDA(cudaEventRecord(c->ev_in, st));                 // inputs are ready here
-    if (march(c, mode, A, st, 0, el)) return -1;
-    if (march(c, mode, A, st, nex - er, nex)) return -1;
-    if (post && post()) return -1;
     SEM_CUDA(cudaStreamWaitEvent(c->s_side, c->ev_in, 0));
-    if (march(c, mode, A, c->s_side, el, nex - er)) return -1;
+    if (march(c, mode, A, st, 0, el)) return -1;             // left edge on the caller's stream ...
+    if (march(c, mode, A, c->s_side, nex - er, nex)) return -1;   // ... right edge concurrently on the side stream
+    SEM_CUDA(cudaEventRecord(c->ev_edge, c->s_side));
+    if (march(c, mode, A, c->s_side, el, nex - er)) return -1;    // interior behind it
     SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
+    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_edge, 0));
+    if (post && post()) return -1;
     if (comm_exchange_transfer(c->comm, c->g, f, n, st)) return -1;
     SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
     if (post && post()) return -1;
