@@ -68,7 +68,8 @@ typedef struct {
     double atol;           /* stop when the true residual 2-norm <= atol */
     int restart;           /* Krylov basis size per cycle */
     int max_iters;         /* total iteration cap */
-    int precond;           /* 0 none, 1 Jacobi (CD) ; NS: block lower-triangular, see DESIGN.md */
+    int precond;           /* 0 none, 1 Jacobi, 2 fast diagonalisation (needs sem_ctx_set_fdm); NS: block lower-
+                              triangular with that velocity block, see DESIGN.md */
     int verbose;
     /* outputs */
     int iters;             /* operator applications spent */
@@ -87,6 +88,14 @@ int sem_ctx_ny(const sem_ctx *ctx);            /* N_ey*P+1 */
 long long sem_ctx_vec_len(const sem_ctx *ctx); /* doubles per vec = NX_local*LD */
 /* launch tuning: elements per strip in y and per marching chunk in x (0 = automatic) */
 int sem_ctx_set_tiling(sem_ctx *ctx, int Ty, int Mx);
+
+/* ---- fast-diagonalisation (FDM) preconditioner of the Krylov solvers (sem_krylov.precond = 2) ----------------------
+ * Qx: DEVICE, row-major [NX][NX], column k = k-th generalised eigenvector of the assembled 1-D pencil (K1x, M1x) with the
+ * Dirichlet end nodes eliminated (their rows, and the unused trailing columns, are zero), normalised Qx^T M1x Qx = I;
+ * lamx[NX]: the eigenvalues (1 for unused columns); Qy, lamy likewise for y.  dirichlet_wesn[4]: which sides carry
+ * Dirichlet rows.  The arrays are copied.  Whole mesh on one GPU only. */
+int sem_ctx_set_fdm(sem_ctx *ctx, const double *Qx, const double *lamx, const double *Qy, const double *lamy,
+                    const int *dirichlet_wesn);
 
 /* ---- multi-GPU: one process per GPU, element columns [m_begin, m_end) per rank (sem_mesh_desc).  Rank 0 creates a
  * 128-byte NCCL unique id, the caller distributes it (torch.distributed), every rank attaches.  Afterwards every operator

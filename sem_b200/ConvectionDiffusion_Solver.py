@@ -17,12 +17,13 @@ from .device import SemDevice
 class ConvectionDiffusionSolver:
     def __init__(self, L_x: float, L_y: float, Pe: float, P: int, N_ex: int, N_ey: int,
                  T_W: float = None, T_E: float = None, T_S: float = None, T_N: float = None,
-                 mtol=1e-7, iprint: list = [], device: int = None, restart: int = None, precond: str = 'jacobi',
+                 mtol=1e-7, iprint: list = [], device: int = None, restart: int = None, precond: str = 'auto',
                  partition=None):
         """
         Steady convection-diffusion ``Pe [u, v].grad T = lap T`` on [0,L_x]x[0,L_y] with Dirichlet (value) or
         homogeneous Neumann (None) sides -- arguments as CD:10-35.  Extra, optional: ``device`` (CUDA ordinal),
-        ``restart`` (Krylov basis size), ``precond`` ('jacobi' | 'none'), ``partition`` = (rank, world): this process
+        ``restart`` (Krylov basis size), ``precond`` ('auto' | 'fdm' | 'jacobi' | 'none'; auto = fast diagonalisation of
+        the Laplacian on one GPU, Jacobi on a partitioned mesh), ``partition`` = (rank, world): this process
         owns one strip of element columns and takes/returns the matching slab of every global vector.
         """
         self._iprint = iprint
@@ -49,7 +50,9 @@ class ConvectionDiffusionSolver:
         self._have_jac = False
         self._buf = [d.zeros() for _ in range(4)]
         self._restart = restart
-        self._precond = {'none': 0, 'jacobi': 1}[precond]
+        if precond == 'auto':
+            precond = 'fdm' if partition is None or int(partition[1]) == 1 else 'jacobi'
+        self._precond = {'none': 0, 'jacobi': 1, 'fdm': 2}[precond]
         self._work = None
         self.last_iters = 0
         self.last_resnorm = float('nan')
@@ -87,6 +90,8 @@ class ConvectionDiffusionSolver:
         need = self._lib.sem_cd_work_len(self._dev.ctx, self._restart)
         if self._work is None or self._work.numel() < need:
             self._work = torch.empty(need, dtype=torch.float64, device=self._dev.tdev)
+        if self._precond == 2 and not self._dev.has_fdm:
+            self._dev.setup_fdm([self._bc.active[k] for k in range(4)])
         kr = L.sem_krylov()
         kr.atol = float(self._mtol * np.sqrt(self.N))            # CD:147
         kr.restart = self._restart

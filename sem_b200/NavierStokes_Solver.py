@@ -4,8 +4,8 @@ and the Krylov basis live on the B200; every operation is a call into ``libsem_b
 
 Linear solve.  The reference factorises the velocity block with SuperLU and runs LGMRES on the pressure Schur
 complement with a diagonal-mass right preconditioner (NS:162-236).  Here the whole 3-field system is solved by
-right-preconditioned GMRES with the block lower-triangular preconditioner [[P_a, 0], [C, M_p]] (P_a = Jacobi on the
-velocity block, C = continuity rows, M_p = the reference's mass preconditioner).  The linearised system is singular
+right-preconditioned GMRES with the block lower-triangular preconditioner [[P_a, 0], [C, M_p]] (P_a = the exact inverse
+of the Laplacian by fast diagonalisation, or Jacobi, on the velocity block, C = continuity rows, M_p = the reference's mass preconditioner).  The linearised system is singular
 but consistent on most meshes (equal-order spaces); this structure makes GMRES pick the same member of
 the solution family as the reference's Schur iteration, so pressures agree too.
 """
@@ -24,8 +24,9 @@ class NavierStokesSolver:
     def __init__(self, L_x: float, L_y: float, Re: float, Gr: float, P: int, N_ex: int, N_ey: int,
                  v_W: float = 0, v_E: float = 0, u_S: float = 0, u_N: float = 0,
                  mtol=1e-7, mtol_newton=1e-5, iprint: list = ['NEWTON_suc', 'NEWTON_iter'],
-                 device: int = None, restart: int = None, max_newton: int = 50, partition=None):
-        """Arguments as NS:11-41.  Extra, optional: ``device``, ``restart`` (Krylov basis size), ``max_newton``."""
+                 device: int = None, restart: int = None, max_newton: int = 50, partition=None, precond: str = 'auto'):
+        """Arguments as NS:11-41.  Extra, optional: ``device``, ``restart`` (Krylov basis size), ``max_newton``,
+        ``precond`` of the velocity block ('auto' | 'fdm' | 'jacobi'; auto = fast diagonalisation on one GPU)."""
         self._iprint = iprint
         self._Re = Re
         self._Gr = Gr
@@ -55,6 +56,9 @@ class NavierStokesSolver:
         self._out = d.zeros(3)
         self._x = d.zeros(3)
         self._restart = restart
+        if precond == 'auto':
+            precond = 'fdm' if partition is None or int(partition[1]) == 1 else 'jacobi'
+        self._precond = {'jacobi': 1, 'fdm': 2}[precond]
         self._work = None
         self.last_iters = 0
         self.last_resnorm = float('nan')
@@ -116,7 +120,9 @@ class NavierStokesSolver:
         kr.atol = float(self._mtol * np.sqrt(self.N))            # NS:223
         kr.restart = self._restart
         kr.max_iters = max(2000, 10 * self._restart)
-        kr.precond = 1
+        if self._precond == 2 and not self._dev.has_fdm:
+            self._dev.setup_fdm([1, 1, 1, 1])                    # velocity Dirichlet rows on all four sides (NS:78-88)
+        kr.precond = self._precond
         kr.verbose = 2 if 'LGMRES_iter' in self._iprint else 0
         return kr
 

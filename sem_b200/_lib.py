@@ -69,6 +69,7 @@ SIGNATURES = {
     "sem_cd_residual": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P]),
     "sem_cd_jacobians": (C.c_int, [_P, C.c_double, _P, _P, _P, _P]),
     "sem_cd_jvp": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P, _P, _P]),
+    "sem_ctx_set_fdm": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_int)]),
     "sem_cd_jvp_host": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P, _P, _P]),
     "sem_cd_work_len": (_LL, [_P, C.c_int]),
     "sem_cd_solve": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, C.POINTER(sem_krylov), _P, _LL, _P]),

@@ -449,4 +449,51 @@ int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fast-diagonalisation preconditioner: spectral scaling and Dirichlet pass-through
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_fdm_scale(const MeshDev g, const double* __restrict__ lx, const double* __restrict__ ly,
+                            double* __restrict__ z) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tot = (long long)g.NX * g.LD;
+    if (idx >= tot) return;
+    const int ix = (int)(idx / g.LD), iy = (int)(idx % g.LD);
+    if (iy >= g.NY) return;
+    const double den = lx[ix] + ly[iy];
+    // the constant mode of an all-Neumann Laplacian has lx + ly = 0: pseudo-inverse
+    z[idx] = (den > 1e-12 * (lx[g.NX - 1] + ly[g.NY - 1])) ? z[idx] / den : 0.0;
+}
+
+int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, cudaStream_t st) {
+    const long long tot = (long long)g.NX * g.LD;
+    k_fdm_scale<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, lx, ly, z);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+struct DirFlags { int d[4]; };
+
+// boundary nodes only: threads 0..NY-1 -> line 0, NY..2NY-1 -> last line, then the first / last column of every line
+__global__ void k_fdm_boundary(const MeshDev g, const DirFlags f, const double* __restrict__ r, double* __restrict__ z) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ix, iy;
+    if (t < g.NY) { ix = 0; iy = t; }
+    else if (t < 2 * g.NY) { ix = g.NX - 1; iy = t - g.NY; }
+    else if (t < 2 * g.NY + g.NX) { ix = t - 2 * g.NY; iy = 0; }
+    else if (t < 2 * g.NY + 2 * g.NX) { ix = t - 2 * g.NY - g.NX; iy = g.NY - 1; }
+    else return;
+    const bool dir = (ix == 0 && f.d[SIDE_W]) || (ix == g.NX - 1 && f.d[SIDE_E]) || (iy == 0 && f.d[SIDE_S]) ||
+                     (iy == g.NY - 1 && f.d[SIDE_N]);
+    if (dir) z[(long long)ix * g.LD + iy] = r[(long long)ix * g.LD + iy];
+}
+
+int aux_fdm_boundary(const MeshDev& g, const int* dir_wesn, const double* r, double* z, cudaStream_t st) {
+    DirFlags f;
+    for (int k = 0; k < 4; ++k) f.d[k] = dir_wesn[k];
+    const int tot = 2 * (g.NX + g.NY);
+    k_fdm_boundary<<<(tot + 255) / 256, 256, 0, st>>>(g, f, r, z);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace semb

@@ -6,6 +6,7 @@
 #include "sem_march.cuh"
 #include "sem_march3.cuh"
 #include <cstdlib>
+#include <cublas_v2.h>
 
 #include <cmath>
 #include <algorithm>
@@ -58,6 +59,10 @@ struct sem_ctx {
     double* dStageOut;
     cudaEvent_t ev_up[SEM_HOST_SEGMENTS], ev_done[SEM_HOST_SEGMENTS], ev_start, ev_end;
     int streams_ready;
+    // fast-diagonalisation preconditioner (sem_ctx_set_fdm): 1-D generalised eigenpairs of the x and y pencils
+    cublasHandle_t blas;
+    double *fQx, *fLx, *fQy, *fLy, *fT1, *fT2;
+    int fdm_ready, fdm_dir[4];
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
 };
 
@@ -136,6 +141,8 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     if (c->dStage) cudaFree(c->dStage);
     if (c->has_comm) comm_destroy(c->comm);
     if (c->dStageOut) cudaFree(c->dStageOut);
+    if (c->fQx) { cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2); }
+    if (c->blas) cublasDestroy(c->blas);
     if (c->streams_ready) {
         cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
         cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_edge); cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
@@ -509,6 +516,69 @@ extern "C" int sem_axpby(sem_ctx* c, double a, const double* x, double b, double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Fast-diagonalisation (FDM) preconditioner.  On the reference's meshes (uniform rectangular element grid, SEM.py:170-203)
+// the assembled stiffness matrix is a Kronecker sum of 1-D operators, K = K1x (x) M1y + M1x (x) K1y, and every side is
+// either all Dirichlet or all Neumann, so the Laplacian with the Dirichlet rows eliminated is inverted exactly by the
+// generalised eigenpairs of the two 1-D pencils:   K^-1 = (Qx (x) Qy) diag(1/(lx_i + ly_j)) (Qx (x) Qy)^T,
+// Q^T M1 Q = I, Q^T K1 Q = diag(l).  Four dense fp64 GEMMs (cuBLAS: plain library GEMMs on the tensor cores) + one
+// scaling pass per application; the iteration count of the Krylov solver no longer grows with the mesh.
+// Q is stored row-major [n][n] with zero rows at Dirichlet end nodes, so the result is zero there and the identity rows
+// of the operator are restored by a boundary pass (z = r).
+// ---------------------------------------------------------------------------------------------------------------
+#define SEM_CUBLAS(call)                                                                                   \
+    do {                                                                                                   \
+        cublasStatus_t _s = (call);                                                                        \
+        if (_s != CUBLAS_STATUS_SUCCESS) {                                                                 \
+            set_error(std::string(#call) + " failed with cuBLAS status " + std::to_string((int)_s));      \
+            return -1;                                                                                     \
+        }                                                                                                  \
+    } while (0)
+
+extern "C" int sem_ctx_set_fdm(sem_ctx* c, const double* Qx, const double* lamx, const double* Qy, const double* lamy,
+                               const int* dirichlet_wesn) {
+    SEM_CHECK_CTX(c);
+    if (c->has_comm || c->g.has_left || c->g.has_right) {
+        set_error("sem_ctx_set_fdm: the global fast-diagonalisation preconditioner needs the whole mesh on one GPU");
+        return -2;
+    }
+    const size_t nx = (size_t)c->g.NX, ny = (size_t)c->g.NY, vlen = nx * c->g.LD;
+    if (!c->fQx) {
+        SEM_CUDA(cudaMalloc(&c->fQx, sizeof(double) * nx * nx));
+        SEM_CUDA(cudaMalloc(&c->fLx, sizeof(double) * nx));
+        SEM_CUDA(cudaMalloc(&c->fQy, sizeof(double) * ny * ny));
+        SEM_CUDA(cudaMalloc(&c->fLy, sizeof(double) * ny));
+        SEM_CUDA(cudaMalloc(&c->fT1, sizeof(double) * vlen));
+        SEM_CUDA(cudaMalloc(&c->fT2, sizeof(double) * vlen));
+        SEM_CUDA(cudaMemset(c->fT1, 0, sizeof(double) * vlen));   // the GEMMs never touch the pad columns
+        SEM_CUDA(cudaMemset(c->fT2, 0, sizeof(double) * vlen));
+    }
+    if (!c->blas) SEM_CUBLAS(cublasCreate(&c->blas));
+    SEM_CUDA(cudaMemcpy(c->fQx, Qx, sizeof(double) * nx * nx, cudaMemcpyDeviceToDevice));
+    SEM_CUDA(cudaMemcpy(c->fLx, lamx, sizeof(double) * nx, cudaMemcpyDeviceToDevice));
+    SEM_CUDA(cudaMemcpy(c->fQy, Qy, sizeof(double) * ny * ny, cudaMemcpyDeviceToDevice));
+    SEM_CUDA(cudaMemcpy(c->fLy, lamy, sizeof(double) * ny, cudaMemcpyDeviceToDevice));
+    for (int k = 0; k < 4; ++k) c->fdm_dir[k] = dirichlet_wesn[k];
+    c->fdm_ready = 1;
+    return 0;
+}
+
+// z = K_II^-1 r on the nodes that carry no Dirichlet row, z = r on the Dirichlet nodes.  r and z may not alias.
+static int fdm_apply(sem_ctx* c, const double* r, double* z, cudaStream_t st) {
+    if (!c->fdm_ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called"); return -2; }
+    const int nx = c->g.NX, ny = c->g.NY, ld = c->g.LD;
+    const double one = 1.0, zero = 0.0;
+    SEM_CUBLAS(cublasSetStream(c->blas, st));
+    // a row-major [NX][LD] vec is the column-major matrix R^T (ny x nx, leading dimension LD); a row-major Q is the
+    // column-major Q^T.  Steps: T1 = Qx^T R, Z = T1 Qy, Z /= (lx + ly), T2 = Z Qy^T, X = Qx T2 -- written for the transposes.
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nx, nx, &one, r, ld, c->fQx, nx, &zero, c->fT1, ld));
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT1, ld, &zero, c->fT2, ld));
+    if (aux_fdm_scale(c->g, c->fLx, c->fLy, c->fT2, st)) return -1;
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT2, ld, &zero, c->fT1, ld));
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nx, &one, c->fT1, ld, c->fQx, nx, &zero, z, ld));
+    return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Right-preconditioned restarted GMRES with CGS2 orthogonalisation (two classical Gram-Schmidt passes, each one
 // batched dot kernel + one batched update kernel).  Replaces scipy.sparse.linalg.lgmres of CD:146-148 / NS:222-224.
 // The stopping rule is the reference's: true residual 2-norm <= atol (right preconditioning keeps the Arnoldi
@@ -643,6 +713,7 @@ extern "C" int sem_cd_solve(sem_ctx* c, const sem_cd_state* s, const double* rhs
     vecop Aop = [&](const double* xx, double* yy) { return sem_cd_jvp(c, &lin, xx, nullptr, nullptr, yy, stream); };
     vecop Pinv = [&](const double* r, double* z) {
         if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, vlen, st);
+        if (kr->precond == 2) return fdm_apply(c, r, z, st);
         return aux_cd_jacobi(c->g, bc, c->dKdiag, r, z, st);
     };
     GmresLayout L{vlen, 1, vlen};
@@ -678,7 +749,11 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
     // solution family as the reference's Schur-complement iteration -- see DESIGN.md.
     vecop Pinv = [&](const double* r, double* z) {
         if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, n, st);
-        if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) return -1;
+        if (kr->precond == 2) {
+            if (fdm_apply(c, r, z, st) || fdm_apply(c, r + vlen, z + vlen, st)) return -1;
+        } else if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) {
+            return -1;
+        }
         MarchArgs A = zero_args();
         A.a = z; A.b = z + vlen; A.y0 = tmp;
         if (apply_and_exchange(c, MODE_DIV, A, {tmp}, st)) return -1;

@@ -82,6 +82,7 @@ class SemDevice:
         self.vec_len = self.lib.sem_ctx_vec_len(ctx)
         self.N_local = self.NX * self.NY
         self._pinned = {}
+        self.has_fdm = False
         if self.part is not None and self.part.world > 1:
             self._attach_comm()
 
@@ -146,6 +147,43 @@ class SemDevice:
             out = _pinned_result(self.N_local)
         L.check(self.lib.sem_d2h(self.ctx, vec.data_ptr(), out.ctypes.data, self.stream), "sem_d2h")
         return out
+
+    # ---- fast-diagonalisation preconditioner ---------------------------------------------------------------------------
+    def _fdm_1d(self, nel, h, dir_lo, dir_hi):
+        """Generalised eigenpairs of the assembled 1-D pencil (K1, M1) of ``nel`` elements of size ``h`` (SEM.py:186-203
+        restricted to one direction) with the Dirichlet end nodes eliminated.  Returns (Q [n, n] row-major with zero
+        rows at eliminated nodes and zero unused columns, lam [n]) on the device: Q^T M1 Q = I, Q^T K1 Q = diag(lam)."""
+        P, n = self.P, nel * self.P + 1
+        Ks = torch.from_numpy(self._Ks).to(self.tdev) * (2.0 / h)
+        w = torch.from_numpy(self._w).to(self.tdev) * (0.5 * h)
+        rows = (torch.arange(nel, device=self.tdev)[:, None] * P + torch.arange(P + 1, device=self.tdev)[None, :])
+        K = torch.zeros((n, n), dtype=torch.float64, device=self.tdev)
+        flat = (rows[:, :, None] * n + rows[:, None, :]).reshape(-1)
+        K.view(-1).index_add_(0, flat, Ks.expand(nel, P + 1, P + 1).reshape(-1))
+        M = torch.zeros(n, dtype=torch.float64, device=self.tdev)
+        M.index_add_(0, rows.reshape(-1), w.expand(nel, P + 1).reshape(-1))
+        lo, hi = (1 if dir_lo else 0), (n - 1 if dir_hi else n)
+        s = 1.0 / torch.sqrt(M[lo:hi])
+        A = K[lo:hi, lo:hi] * s[:, None] * s[None, :]
+        lam, V = torch.linalg.eigh(0.5 * (A + A.T))
+        Q = torch.zeros((n, n), dtype=torch.float64, device=self.tdev)
+        Q[lo:hi, :hi - lo] = V * s[:, None]
+        lam_full = torch.ones(n, dtype=torch.float64, device=self.tdev)
+        lam_full[:hi - lo] = lam.clamp_min(0.0)
+        return Q.contiguous(), lam_full
+
+    def setup_fdm(self, dirichlet_wesn):
+        """Build and hand over the fast-diagonalisation preconditioner for the given Dirichlet sides (W, E, S, N)."""
+        if self.part is not None and self.part.world > 1:
+            raise L.SemError("the fast-diagonalisation preconditioner needs the whole mesh on one GPU")
+        dW, dE, dS, dN = (bool(v) for v in dirichlet_wesn)
+        Qx, lx = self._fdm_1d(self.N_ex, self.dx, dW, dE)
+        Qy, ly = self._fdm_1d(self.N_ey, self.dy, dS, dN)
+        flags = (C.c_int * 4)(int(dW), int(dE), int(dS), int(dN))
+        torch.cuda.current_stream(self.tdev).synchronize()
+        L.check(self.lib.sem_ctx_set_fdm(self.ctx, Qx.data_ptr(), lx.data_ptr(), Qy.data_ptr(), ly.data_ptr(), flags),
+                "sem_ctx_set_fdm")
+        self.has_fdm = True
 
     # ---- single operators ------------------------------------------------------------------------------------------
     def apply_stiffness(self, x, y):
