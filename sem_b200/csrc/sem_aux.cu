@@ -302,49 +302,100 @@ int aux_multi_dot(const double* V, long long n, int k, const double* w, double* 
 constexpr int AXPY_THREADS = 256;
 constexpr int AXPY_HT = 128;   // coefficients staged per tile
 
-template <bool COMB>
-__global__ void __launch_bounds__(AXPY_THREADS) k_multi_axpy(const double* __restrict__ V, long long n, int k,
-                                                             const double* __restrict__ h, double sign,
-                                                             double* __restrict__ w) {
-    __shared__ double sh[AXPY_HT];
-    const long long e = (long long)blockIdx.x * AXPY_THREADS + threadIdx.x;
-    double acc = 0.0;
-    for (int j0 = 0; j0 < k; j0 += AXPY_HT) {
-        const int nj = min(AXPY_HT, k - j0);
+// acc = sum over the basis vectors j in [ja, jb) of h[j] * V_j[e]  (fixed order; two accumulators for load parallelism)
+__device__ __forceinline__ double axpy_partial(const double* __restrict__ V, long long n, const double* __restrict__ h,
+                                               int ja, int jb, long long e, bool active, double* sh) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int j0 = ja; j0 < jb; j0 += AXPY_HT) {
+        const int nj = min(AXPY_HT, jb - j0);
         __syncthreads();
         if (threadIdx.x < nj) sh[threadIdx.x] = h[j0 + threadIdx.x];
         __syncthreads();
-        if (e < n) {
+        if (active) {
+            int q = 0;
 #pragma unroll 4
-            for (int q = 0; q < nj; ++q) acc = fma(sh[q], V[(long long)(j0 + q) * n + e], acc);
+            for (; q + 1 < nj; q += 2) {
+                a0 = fma(sh[q], V[(long long)(j0 + q) * n + e], a0);
+                a1 = fma(sh[q + 1], V[(long long)(j0 + q + 1) * n + e], a1);
+            }
+            if (q < nj) a0 = fma(sh[q], V[(long long)(j0 + q) * n + e], a0);
         }
     }
-    if (e < n) w[e] = COMB ? acc : fma(sign, acc, w[e]);
+    return a0 + a1;
 }
 
-int aux_multi_axpy(const double* V, long long n, int k, const double* h, double sign, double* w, cudaStream_t st) {
+// w -= / += V h (COMB: w = V h).  grid.y = J slices of the basis: on the reference's small meshes one thread per element
+// leaves the GPU almost empty (15 k elements, 600 vectors: 37 us), so the sum over j is split, the slices' partial sums go
+// to scratch and the last slice to finish an element block (integer ticket) adds them in slice order -- deterministic.
+template <bool COMB>
+__global__ void __launch_bounds__(AXPY_THREADS) k_multi_axpy(const double* __restrict__ V, long long n, int k,
+                                                             const double* __restrict__ h, double sign,
+                                                             double* __restrict__ w, double* __restrict__ partials,
+                                                             unsigned* __restrict__ counter) {
+    __shared__ double sh[AXPY_HT];
+    const long long e = (long long)blockIdx.x * AXPY_THREADS + threadIdx.x;
+    const int J = gridDim.y, jc = blockIdx.y;
+    const int per = (k + J - 1) / J;
+    const int ja = min(k, jc * per), jb = min(k, ja + per);
+    const double acc = axpy_partial(V, n, h, ja, jb, e, e < n, sh);
+    if (J == 1) {
+        if (e < n) w[e] = COMB ? acc : fma(sign, acc, w[e]);
+        return;
+    }
+    if (e < n) partials[(long long)jc * n + e] = acc;
+    __shared__ unsigned ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(&counter[blockIdx.x], 1u);
+    __syncthreads();
+    if (ticket == (unsigned)(J - 1)) {
+        __threadfence();
+        if (e < n) {
+            double v = 0.0;
+            for (int q = 0; q < J; ++q) v += partials[(long long)q * n + e];
+            w[e] = COMB ? v : fma(sign, v, w[e]);
+        }
+        if (threadIdx.x == 0) counter[blockIdx.x] = 0u;
+    }
+}
+
+template <bool COMB>
+static int launch_multi_axpy(const double* V, long long n, int k, const double* h, double sign, double* w, RedScratch rs,
+                             cudaStream_t st) {
+    const long long nb = (n + AXPY_THREADS - 1) / AXPY_THREADS;
+    // enough slices for ~4 blocks per SM, at least 32 vectors per slice, bounded by the scratch
+    long long J = (4ll * rs.sm_count + nb - 1) / nb;
+    if (J > (k + 31) / 32) J = (k + 31) / 32;
+    if (J > 16) J = 16;
+    if (J < 1 || nb > rs.axpy_blocks || J * n > rs.axpy_len) J = 1;
+    dim3 grid((unsigned)nb, (unsigned)J);
+    k_multi_axpy<COMB><<<grid, AXPY_THREADS, 0, st>>>(V, n, k, h, sign, w, rs.axpy_partials, rs.axpy_counter);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int aux_multi_axpy(const double* V, long long n, int k, const double* h, double sign, double* w, RedScratch rs,
+                   cudaStream_t st) {
     if (k <= 0) return 0;
-    k_multi_axpy<false><<<(unsigned)((n + AXPY_THREADS - 1) / AXPY_THREADS), AXPY_THREADS, 0, st>>>(V, n, k, h, sign, w);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
+    return launch_multi_axpy<false>(V, n, k, h, sign, w, rs, st);
 }
 
-int aux_multi_comb(const double* V, long long n, int k, const double* h, double* out, cudaStream_t st) {
-    k_multi_axpy<true><<<(unsigned)((n + AXPY_THREADS - 1) / AXPY_THREADS), AXPY_THREADS, 0, st>>>(V, n, k, h, 1.0, out);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
+int aux_multi_comb(const double* V, long long n, int k, const double* h, double* out, RedScratch rs, cudaStream_t st) {
+    return launch_multi_axpy<true>(V, n, k, h, 1.0, out, rs, st);
 }
 
 __global__ void k_scale_inv_norm(const double* __restrict__ w, const double* __restrict__ nrm2, double* __restrict__ v,
-                                 long long n) {
+                                 double* __restrict__ v2, long long n) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const double s = 1.0 / sqrt(*nrm2);
-    v[e] = w[e] * s;
+    const double r = w[e] * s;
+    v[e] = r;
+    if (v2) v2[e] = r;
 }
 
-int aux_scale_inv_norm(const double* w, const double* nrm2, double* v, long long n, cudaStream_t st) {
-    k_scale_inv_norm<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, nrm2, v, n);
+int aux_scale_inv_norm(const double* w, const double* nrm2, double* v, double* v2, long long n, cudaStream_t st) {
+    k_scale_inv_norm<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, nrm2, v, v2, n);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -38,6 +38,12 @@ struct RedScratch {
     unsigned* counter;  // device, zero-initialised ticket
     int max_blocks;
     int max_k;
+    // multi_axpy: partial sums of the basis slices [slice][n] (used when n is small), one ticket per element block
+    double* axpy_partials;
+    unsigned* axpy_counter;
+    long long axpy_len;
+    int axpy_blocks;
+    int sm_count;
 };
 
 // h[j] = <V_j, w>, j = 0..k-1, V_j = V + j*n.  Two-stage deterministic sum (fixed block order, no float atomics).
@@ -45,11 +51,12 @@ struct RedScratch {
 int aux_multi_dot(const double* V, long long n, int k, const double* w, double* h, int nf, long long vlen,
                   long long skip, RedScratch rs, cudaStream_t st);
 // w += sign * sum_j h[j] V_j   (h on the device)
-int aux_multi_axpy(const double* V, long long n, int k, const double* h, double sign, double* w, cudaStream_t st);
+int aux_multi_axpy(const double* V, long long n, int k, const double* h, double sign, double* w, RedScratch rs,
+                   cudaStream_t st);
 // out = sum_j h[j] V_j
-int aux_multi_comb(const double* V, long long n, int k, const double* h, double* out, cudaStream_t st);
-// v = w / sqrt(*nrm2)
-int aux_scale_inv_norm(const double* w, const double* nrm2, double* v, long long n, cudaStream_t st);
+int aux_multi_comb(const double* V, long long n, int k, const double* h, double* out, RedScratch rs, cudaStream_t st);
+// v = w / sqrt(*nrm2); v2 (optional) receives a second copy
+int aux_scale_inv_norm(const double* w, const double* nrm2, double* v, double* v2, long long n, cudaStream_t st);
 // y = a*x + b*y   (b == 0: y = a*x without reading y)
 int aux_axpby(double a, const double* x, double b, double* y, long long n, cudaStream_t st);
 

@@ -56,11 +56,13 @@ struct sem_ctx {
     cudaEvent_t ev_in, ev_edge, ev_side;
     // host-buffer pipeline (sem_cd_jvp_host): upload / download streams, second staging buffer, per-segment events
     cudaStream_t s_h2d, s_d2h;
+    cudaStream_t s_solve;    // the Krylov solvers run here: CUDA graphs cannot be captured on the legacy default stream
     double* dStageOut;
     cudaEvent_t ev_up[SEM_HOST_SEGMENTS], ev_done[SEM_HOST_SEGMENTS], ev_start, ev_end;
     int streams_ready;
     // fast-diagonalisation preconditioner (sem_ctx_set_fdm): 1-D generalised eigenpairs of the x and y pencils
     cublasHandle_t blas;
+    void* blas_ws;
     double *fQx, *fLx, *fQy, *fLy, *fT1, *fT2;
     int fdm_ready, fdm_dir[4];
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
@@ -126,6 +128,12 @@ extern "C" int sem_ctx_create(sem_ctx** out, const sem_mesh_desc* d) {
     SEM_CUDA(cudaMalloc(&c->rs.partials, sizeof(double) * (size_t)c->rs.max_blocks * c->rs.max_k));
     SEM_CUDA(cudaMalloc(&c->rs.counter, sizeof(unsigned) * (c->rs.max_k / 8 + 1)));
     SEM_CUDA(cudaMemset(c->rs.counter, 0, sizeof(unsigned) * (c->rs.max_k / 8 + 1)));
+    c->rs.sm_count = c->sm_count;
+    c->rs.axpy_blocks = 4096;                 // element blocks of 256: slices are used up to n = 1 M doubles
+    c->rs.axpy_len = 4ll << 20;               // 4 M doubles of partial sums (32 MB)
+    SEM_CUDA(cudaMalloc(&c->rs.axpy_partials, sizeof(double) * c->rs.axpy_len));
+    SEM_CUDA(cudaMalloc(&c->rs.axpy_counter, sizeof(unsigned) * c->rs.axpy_blocks));
+    SEM_CUDA(cudaMemset(c->rs.axpy_counter, 0, sizeof(unsigned) * c->rs.axpy_blocks));
     c->small_len = 2 * SEM_MAX_RESTART + 64;
     SEM_CUDA(cudaMalloc(&c->d_small, sizeof(double) * c->small_len));
     SEM_CUDA(cudaMallocHost(&c->h_small, sizeof(double) * c->small_len));
@@ -142,13 +150,13 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     if (c->has_comm) comm_destroy(c->comm);
     if (c->dStageOut) cudaFree(c->dStageOut);
     if (c->fQx) { cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2); }
-    if (c->blas) cublasDestroy(c->blas);
+    if (c->blas) { cublasDestroy(c->blas); cudaFree(c->blas_ws); }
     if (c->streams_ready) {
-        cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
+        cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_solve);
         cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_edge); cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
         for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
     }
-    cudaFree(c->rs.partials); cudaFree(c->rs.counter);
+    cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->rs.axpy_partials); cudaFree(c->rs.axpy_counter);
     cudaFree(c->d_small); cudaFreeHost(c->h_small);
     delete c;
 }
@@ -259,6 +267,7 @@ static int ensure_streams(sem_ctx* c) {
     SEM_CUDA(cudaStreamCreateWithPriority(&c->s_side, cudaStreamNonBlocking, lo));
     SEM_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     SEM_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    SEM_CUDA(cudaStreamCreateWithFlags(&c->s_solve, cudaStreamNonBlocking));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
@@ -301,12 +310,24 @@ static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializ
     if (ensure_streams(c)) return -1;
     SEM_CUDA(cudaEventRecord(c->ev_in, st));                 // inputs are ready here
     SEM_CUDA(cudaStreamWaitEvent(c->s_side, c->ev_in, 0));
-    if (march(c, mode, A, st, 0, el)) return -1;             // left edge on the caller's stream ...
-    if (march(c, mode, A, c->s_side, nex - er, nex)) return -1;   // ... right edge concurrently on the side stream
-    SEM_CUDA(cudaEventRecord(c->ev_edge, c->s_side));
-    if (march(c, mode, A, c->s_side, el, nex - er)) return -1;    // interior behind it
-    SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
-    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_edge, 0));
+    // A large interior (several resident rounds of one-warp CTAs) goes first: it starts at once, and the edge launches on
+    // the higher-priority caller's stream slip in as soon as its first CTAs retire -- long before it ends.  A small interior
+    // (8 GPUs on config 5: about one round) would delay the edges past its own end, so there the edges go first.
+    const long long interior_ctas = (long long)(c->g.ney / 8 + 1) * ((nex - el - er + 15) / 16);
+    const bool interior_first = interior_ctas >= 3ll * 6 * c->sm_count;
+    if (interior_first) {
+        if (march(c, mode, A, c->s_side, el, nex - er)) return -1;
+        SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
+        if (march(c, mode, A, st, 0, el)) return -1;
+        if (march(c, mode, A, st, nex - er, nex)) return -1;
+    } else {
+        if (march(c, mode, A, st, 0, el)) return -1;             // left edge on the caller's stream ...
+        if (march(c, mode, A, c->s_side, nex - er, nex)) return -1;   // ... right edge concurrently on the side stream
+        SEM_CUDA(cudaEventRecord(c->ev_edge, c->s_side));
+        if (march(c, mode, A, c->s_side, el, nex - er)) return -1;    // interior behind it
+        SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
+        SEM_CUDA(cudaStreamWaitEvent(st, c->ev_edge, 0));
+    }
     if (post && post()) return -1;
     if (comm_exchange_transfer(c->comm, c->g, f, n, st)) return -1;
     SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
@@ -552,7 +573,11 @@ extern "C" int sem_ctx_set_fdm(sem_ctx* c, const double* Qx, const double* lamx,
         SEM_CUDA(cudaMemset(c->fT1, 0, sizeof(double) * vlen));   // the GEMMs never touch the pad columns
         SEM_CUDA(cudaMemset(c->fT2, 0, sizeof(double) * vlen));
     }
-    if (!c->blas) SEM_CUBLAS(cublasCreate(&c->blas));
+    if (!c->blas) {
+        SEM_CUBLAS(cublasCreate(&c->blas));
+        SEM_CUDA(cudaMalloc(&c->blas_ws, (size_t)32 << 20));   // fixed workspace: the GEMMs are captured into CUDA graphs
+        SEM_CUBLAS(cublasSetWorkspace(c->blas, c->blas_ws, (size_t)32 << 20));
+    }
     SEM_CUDA(cudaMemcpy(c->fQx, Qx, sizeof(double) * nx * nx, cudaMemcpyDeviceToDevice));
     SEM_CUDA(cudaMemcpy(c->fLx, lamx, sizeof(double) * nx, cudaMemcpyDeviceToDevice));
     SEM_CUDA(cudaMemcpy(c->fQy, Qy, sizeof(double) * ny * ny, cudaMemcpyDeviceToDevice));
@@ -593,7 +618,7 @@ struct GmresLayout {
 };
 
 static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop& Pinv, const double* b, double* x,
-                 sem_krylov* kr, double* V, double* w, double* t, cudaStream_t st) {
+                 sem_krylov* kr, double* V, double* w, double* t, double* vin, cudaStream_t st, bool use_graph) {
     const long long n = L.n;
     int m = kr->restart;
     if (m < 1) m = 1;
@@ -615,30 +640,59 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
     double beta;
     if (norm2(V, &beta)) return -1;
     if (kr->verbose) fprintf(stderr, "[sem gmres] start |r| = %.6e  atol = %.3e  n = %lld restart = %d\n", beta, kr->atol, n, m);
+    // The fixed part of an iteration, w = A Pinv(vin) (~17 launches for NS), is captured once into a CUDA graph and
+    // replayed: on the reference's meshes an iteration is launch bound.  vin is a second copy of the newest basis vector
+    // at a fixed address (the graph's kernel arguments never change).
+    cudaGraphExec_t gexec = nullptr;
+    int eager_applies = 0;
+    struct GraphGuard { cudaGraphExec_t* g; ~GraphGuard() { if (*g) cudaGraphExecDestroy(*g); } } guard{&gexec};
+    auto apply_fixed = [&]() -> int {
+        if (gexec) { SEM_CUDA(cudaGraphLaunch(gexec, st)); return 0; }
+        if (!use_graph || eager_applies < 1) {   // the first application also sets every lazily configured kernel attribute
+            ++eager_applies;
+            if (Pinv(vin, t)) return -1;
+            return Aop(t, w);
+        }
+        cudaGraph_t graph = nullptr;
+        SEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = Pinv(vin, t) || Aop(t, w);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc || ce != cudaSuccess || !graph) {   // not capturable here: carry on without a graph
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            use_graph = false;
+            if (Pinv(vin, t)) return -1;
+            return Aop(t, w);
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { gexec = nullptr; cudaGetLastError(); use_graph = false; if (Pinv(vin, t)) return -1; return Aop(t, w); }
+        SEM_CUDA(cudaGraphLaunch(gexec, st));
+        return 0;
+    };
     while (true) {
         kr->resnorm = beta;
         if (!(beta > kr->atol)) return 0;
         if (kr->iters >= kr->max_iters) return kr->iters > 0 ? kr->iters : 1;
         if (aux_axpby(1.0 / beta, V, 0.0, w, n, st)) return -1;
         if (aux_axpby(1.0, w, 0.0, V, n, st)) return -1;
+        if (aux_axpby(1.0, w, 0.0, vin, n, st)) return -1;
         gv.assign(m + 1, 0.0);
         gv[0] = beta;
         int j = 0;
         double est = beta;
         for (; j < m; ++j) {
-            const double* Vj = V + (long long)j * n;
-            if (Pinv(Vj, t)) return -1;
-            if (Aop(t, w)) return -1;
+            if (apply_fixed()) return -1;   // w = A Pinv(V_j), V_j read through its copy vin
             kr->iters++;
             double* h1 = c->d_small;
             double* h2 = c->d_small + (j + 1);
             double* nr = c->d_small + 2 * (j + 1);
             if (ctx_multi_dot(c, V, n, j + 1, w, h1, L.nf, L.vlen, st)) return -1;
-            if (aux_multi_axpy(V, n, j + 1, h1, -1.0, w, st)) return -1;
+            if (aux_multi_axpy(V, n, j + 1, h1, -1.0, w, c->rs, st)) return -1;
             if (ctx_multi_dot(c, V, n, j + 1, w, h2, L.nf, L.vlen, st)) return -1;
-            if (aux_multi_axpy(V, n, j + 1, h2, -1.0, w, st)) return -1;
+            if (aux_multi_axpy(V, n, j + 1, h2, -1.0, w, c->rs, st)) return -1;
             if (ctx_multi_dot(c, w, n, 1, w, nr, L.nf, L.vlen, st)) return -1;
-            if (aux_scale_inv_norm(w, nr, V + (long long)(j + 1) * n, n, st)) return -1;
+            if (aux_scale_inv_norm(w, nr, V + (long long)(j + 1) * n, vin, n, st)) return -1;
             SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double) * (2 * (j + 1) + 1), cudaMemcpyDeviceToHost, st));
             SEM_CUDA(cudaStreamSynchronize(st));
             double* Hj = &H[(size_t)j * (m + 1)];   // column j
@@ -672,7 +726,7 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
         }
         std::memcpy(c->h_small, yv.data(), sizeof(double) * k);
         SEM_CUDA(cudaMemcpyAsync(c->d_small, c->h_small, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        if (aux_multi_comb(V, n, k, c->d_small, w, st)) return -1;
+        if (aux_multi_comb(V, n, k, c->d_small, w, c->rs, st)) return -1;
         if (Pinv(w, t)) return -1;
         if (aux_axpby(1.0, t, 1.0, x, n, st)) return -1;
         // true residual
@@ -690,15 +744,32 @@ static int ensure_kdiag(sem_ctx* c, cudaStream_t st) {
     return aux_stiffness_diag(c->g, c->tab(), c->dKdiag, st);
 }
 
+// The Krylov solvers run on a context-owned non-blocking stream (a CUDA graph cannot be captured on the legacy default
+// stream a caller may hand in); it is ordered after the caller's stream on entry and drained before returning.  With a
+// communicator (NCCL calls, side streams) the caller's stream is used directly and no graph is built.
+static int solve_stream(sem_ctx* c, cudaStream_t user, cudaStream_t* st, bool* use_graph) {
+    static const bool no_graph = std::getenv("SEM_B200_NO_GRAPH") != nullptr;
+    *use_graph = !c->has_comm && !no_graph;
+    *st = user;
+    if (!*use_graph) return 0;
+    if (ensure_streams(c)) return -1;
+    SEM_CUDA(cudaEventRecord(c->ev_start, user));
+    SEM_CUDA(cudaStreamWaitEvent(c->s_solve, c->ev_start, 0));
+    *st = c->s_solve;
+    return 0;
+}
+
 extern "C" long long sem_cd_work_len(const sem_ctx* c, int restart) {
     if (!c) return -1;
-    return (long long)(restart + 1 + 2) * c->g.NX * c->g.LD;
+    return (long long)(restart + 1 + 3) * c->g.NX * c->g.LD;
 }
 
 extern "C" int sem_cd_solve(sem_ctx* c, const sem_cd_state* s, const double* rhs, double* dT, sem_krylov* kr,
                             double* work, long long work_len, void* stream) {
     SEM_CHECK_CTX(c);
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st;
+    bool use_graph;
+    if (solve_stream(c, (cudaStream_t)stream, &st, &use_graph)) return -1;
     const long long vlen = (long long)c->g.NX * c->g.LD;
     if (kr->restart > SEM_MAX_RESTART) kr->restart = SEM_MAX_RESTART;
     if (work_len < sem_cd_work_len(c, kr->restart)) { set_error("sem_cd_solve: work buffer too small"); return -2; }
@@ -706,29 +777,34 @@ extern "C" int sem_cd_solve(sem_ctx* c, const sem_cd_state* s, const double* rhs
     double* V = work;
     double* w = work + (long long)(kr->restart + 1) * vlen;
     double* t = w + vlen;
-    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * 2 * vlen, st));
+    double* vin = t + vlen;
+    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * 3 * vlen, st));
     sem_cd_state lin = *s;
     BCSpec bc;
     fill_cd_bc(bc, s->bc, 0);
-    vecop Aop = [&](const double* xx, double* yy) { return sem_cd_jvp(c, &lin, xx, nullptr, nullptr, yy, stream); };
+    vecop Aop = [&](const double* xx, double* yy) { return sem_cd_jvp(c, &lin, xx, nullptr, nullptr, yy, (void*)st); };
     vecop Pinv = [&](const double* r, double* z) {
         if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, vlen, st);
         if (kr->precond == 2) return fdm_apply(c, r, z, st);
         return aux_cd_jacobi(c->g, bc, c->dKdiag, r, z, st);
     };
     GmresLayout L{vlen, 1, vlen};
-    return gmres(c, L, Aop, Pinv, rhs, dT, kr, V, w, t, st);
+    const int rc = gmres(c, L, Aop, Pinv, rhs, dT, kr, V, w, t, vin, st, use_graph);
+    SEM_CUDA(cudaStreamSynchronize(st));
+    return rc;
 }
 
 extern "C" long long sem_ns_work_len(const sem_ctx* c, int restart) {
     if (!c) return -1;
-    return ((long long)(restart + 1 + 2) * 3 + 1) * c->g.NX * c->g.LD;
+    return ((long long)(restart + 1 + 3) * 3 + 1) * c->g.NX * c->g.LD;
 }
 
 extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs3, double* x3, sem_krylov* kr,
                             double* work, long long work_len, void* stream) {
     SEM_CHECK_CTX(c);
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t st;
+    bool use_graph;
+    if (solve_stream(c, (cudaStream_t)stream, &st, &use_graph)) return -1;
     const long long vlen = (long long)c->g.NX * c->g.LD;
     const long long n = 3 * vlen;
     if (kr->restart > SEM_MAX_RESTART) kr->restart = SEM_MAX_RESTART;
@@ -737,11 +813,12 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
     double* V = work;
     double* w = work + (long long)(kr->restart + 1) * n;
     double* t = w + n;
-    double* tmp = t + n;
-    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (2 * n + vlen), st));
+    double* vin = t + n;
+    double* tmp = vin + n;
+    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (3 * n + vlen), st));
     sem_ns_state lin = *s;
     vecop Aop = [&](const double* xx, double* yy) {
-        return sem_ns_jvp(c, &lin, xx, xx + vlen, xx + 2 * vlen, nullptr, yy, yy + vlen, yy + 2 * vlen, stream);
+        return sem_ns_jvp(c, &lin, xx, xx + vlen, xx + 2 * vlen, nullptr, yy, yy + vlen, yy + 2 * vlen, (void*)st);
     };
     // Block lower-triangular right preconditioner  [[P_a, 0], [C, M_p]]^-1  with P_a = Jacobi on the velocity block,
     // C = continuity rows, M_p = diagonal mass with the pin row passed through (the reference's Schur preconditioner,
@@ -760,5 +837,7 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
         return aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st);
     };
     GmresLayout L{n, 3, vlen};
-    return gmres(c, L, Aop, Pinv, rhs3, x3, kr, V, w, t, st);
+    const int rc = gmres(c, L, Aop, Pinv, rhs3, x3, kr, V, w, t, vin, st, use_graph);
+    SEM_CUDA(cudaStreamSynchronize(st));
+    return rc;
 }

@@ -1,5 +1,6 @@
 #include "sem_comm.cuh"
 
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -111,6 +112,8 @@ __global__ void k_halo_add(const LinePtrs p, int NY) {
 }
 
 int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    static const bool skip = std::getenv("SEM_B200_DEBUG_NO_TRANSFER") != nullptr;   // timing experiments only (wrong results)
+    if (skip) return 0;
     if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
     if (!g.has_left && !g.has_right) return 0;
     ncclComm_t comm = (ncclComm_t)c.nccl;

@@ -765,9 +765,12 @@ inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_
         // 49 columns); shorter chunks, down to 8, only when the mesh is too small to fill the device 4 times over
         const long long slots = (long long)sm_count * resident;
         Mx = 16;
-        while (Mx > 8 && (long long)strips * ((g.nex + Mx - 1) / Mx) < 4 * slots) Mx -= 4;
+        while (Mx > 8 && (long long)strips * ((m_hi - m_lo + Mx - 1) / Mx) < 4 * slots) Mx -= 4;
+        // less than one resident round even then (the reference's own meshes): the launch is pure latency, one warp
+        // marching Mx columns in sequence -- go down to 2 columns per warp
+        while (Mx > 2 && (long long)strips * ((m_hi - m_lo + Mx - 1) / Mx) < slots) Mx -= 2;
     }
-    if (Mx > g.nex) Mx = g.nex;
+    if (Mx > m_hi - m_lo) Mx = m_hi - m_lo;
     q.Ty = EW;
     q.Mx = Mx;
     q.pitch = 0;

@@ -276,3 +276,29 @@ def test_full_size_properties(sem):
     d.axpby(-1.0, Kx, 1.0, Kz)
     d.axpby(2.0, Ky, 1.0, Kz)
     assert np.sqrt(d.dot(Kz, Kz)) <= 1e-12 * np.sqrt(d.dot(Kx, Kx))
+
+
+@pytest.mark.parametrize("bc", [dict(T_W=0.5, T_E=-0.5), dict(T_S=1.0), dict(T_W=0.2, T_E=0.1, T_S=-0.3, T_N=0.4),
+                                dict(T_N=0.5, T_E=0.0)])
+def test_fdm_preconditioner_matches_jacobi_and_is_mesh_independent(sem, bc):
+    """The fast-diagonalisation preconditioner changes the path to the solution, not the solution: same converged field as
+    Jacobi-GMRES (and the oracle's direct solve), for every Dirichlet/Neumann side combination the tensor-product
+    eigen-decomposition has to handle; its iteration count does not grow with the mesh."""
+    from oracle import sem_oracle as so
+    its = []
+    for P, ne in ((4, 6), (4, 24), (8, 48)):
+        kw = dict(L_x=1.3, L_y=0.8, Pe=25.0, P=P, N_ex=ne, N_ey=ne + 1, mtol=1e-12, **bc)
+        cd = sem.ConvectionDiffusionSolver(precond='fdm', **kw)
+        u = cd._get_vector(lambda x, y: y - 0.4)
+        v = cd._get_vector(lambda x, y: 0.65 - x)
+        T = cd._get_solution(u, v)
+        its.append(cd.last_iters)
+        if ne <= 24:
+            assert relerr(T, so.CDOracle(**kw)._get_solution(u, v)) < FIELD_TOL
+            cdj = sem.ConvectionDiffusionSolver(precond='jacobi', **kw)
+            assert relerr(T, cdj._get_solution(u, v)) < FIELD_TOL
+            assert cd.last_iters < cdj.last_iters
+        else:
+            r = cd._get_residuals(T, u, v)
+            assert np.linalg.norm(r) <= 1e-11 * np.sqrt(cd.N)
+    assert max(its) <= 60 and its[-1] <= its[0] + 15
