@@ -37,6 +37,7 @@ static const struct {
 } g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
 
 #define SEM_HOST_SEGMENTS 8   // element-column segments of the host-buffer pipeline
+#define SEM_GMRES_LAG 6       // Arnoldi steps enqueued ahead of the host-side Givens / convergence test
 
 struct sem_ctx {
     MeshDev g;
@@ -50,6 +51,9 @@ struct sem_ctx {
     double* d_small;         // device staging for reduction results
     double* h_small;         // pinned mirror
     int small_len;
+    double* h_ring;          // pinned: SEM_GMRES_LAG slots for the Hessenberg columns in flight
+    size_t ring_stride;
+    cudaEvent_t ev_ring[SEM_GMRES_LAG];
     Comm comm;               // NCCL communicator of the element-column partition (has_comm)
     int has_comm;
     cudaStream_t s_side;     // low-priority stream: the interior of an operator runs here while the interface lines travel
@@ -137,6 +141,9 @@ extern "C" int sem_ctx_create(sem_ctx** out, const sem_mesh_desc* d) {
     c->small_len = 2 * SEM_MAX_RESTART + 64;
     SEM_CUDA(cudaMalloc(&c->d_small, sizeof(double) * c->small_len));
     SEM_CUDA(cudaMallocHost(&c->h_small, sizeof(double) * c->small_len));
+    c->ring_stride = (size_t)c->small_len;
+    SEM_CUDA(cudaMallocHost(&c->h_ring, sizeof(double) * c->ring_stride * SEM_GMRES_LAG));
+    for (int i = 0; i < SEM_GMRES_LAG; ++i) SEM_CUDA(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
     *out = c;
     return 0;
 }
@@ -157,7 +164,8 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
         for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
     }
     cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->rs.axpy_partials); cudaFree(c->rs.axpy_counter);
-    cudaFree(c->d_small); cudaFreeHost(c->h_small);
+    cudaFree(c->d_small); cudaFreeHost(c->h_small); cudaFreeHost(c->h_ring);
+    for (int i = 0; i < SEM_GMRES_LAG; ++i) cudaEventDestroy(c->ev_ring[i]);
     delete c;
 }
 
@@ -679,11 +687,14 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
         if (aux_axpby(1.0, w, 0.0, vin, n, st)) return -1;
         gv.assign(m + 1, 0.0);
         gv[0] = beta;
-        int j = 0;
         double est = beta;
-        for (; j < m; ++j) {
+        // Arnoldi steps are ENQUEUED up to SEM_GMRES_LAG ahead of the host: the Hessenberg column of step j travels to a
+        // pinned ring slot behind an event and is rotated / tested when it arrives, so the GPU never waits for the host
+        // between steps.  A step enqueued past the converged one only writes basis vectors that are not used.
+        int enq = 0, done = 0;
+        bool stop = false;
+        auto enqueue_step = [&](int j) -> int {
             if (apply_fixed()) return -1;   // w = A Pinv(V_j), V_j read through its copy vin
-            kr->iters++;
             double* h1 = c->d_small;
             double* h2 = c->d_small + (j + 1);
             double* nr = c->d_small + 2 * (j + 1);
@@ -693,11 +704,27 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
             if (aux_multi_axpy(V, n, j + 1, h2, -1.0, w, c->rs, st)) return -1;
             if (ctx_multi_dot(c, w, n, 1, w, nr, L.nf, L.vlen, st)) return -1;
             if (aux_scale_inv_norm(w, nr, V + (long long)(j + 1) * n, vin, n, st)) return -1;
-            SEM_CUDA(cudaMemcpyAsync(c->h_small, c->d_small, sizeof(double) * (2 * (j + 1) + 1), cudaMemcpyDeviceToHost, st));
-            SEM_CUDA(cudaStreamSynchronize(st));
+            const int slot = j % SEM_GMRES_LAG;
+            SEM_CUDA(cudaMemcpyAsync(c->h_ring + (size_t)slot * c->ring_stride, c->d_small, sizeof(double) * (2 * (j + 1) + 1),
+                                     cudaMemcpyDeviceToHost, st));
+            SEM_CUDA(cudaEventRecord(c->ev_ring[slot], st));
+            return 0;
+        };
+        while (!stop) {
+            const bool can_enqueue = enq < m && enq - done < SEM_GMRES_LAG && kr->iters + enq < kr->max_iters;
+            if (can_enqueue) {
+                if (enqueue_step(enq)) return -1;
+                ++enq;
+                if (enq - done < SEM_GMRES_LAG && enq < m && kr->iters + enq < kr->max_iters) continue;
+            }
+            if (done == enq) break;   // basis full or iteration cap reached, everything processed
+            const int j = done;
+            const int slot = j % SEM_GMRES_LAG;
+            SEM_CUDA(cudaEventSynchronize(c->ev_ring[slot]));
+            const double* hs = c->h_ring + (size_t)slot * c->ring_stride;
             double* Hj = &H[(size_t)j * (m + 1)];   // column j
-            for (int i = 0; i <= j; ++i) Hj[i] = c->h_small[i] + c->h_small[j + 1 + i];
-            const double hn = std::sqrt(c->h_small[2 * (j + 1)]);
+            for (int i = 0; i <= j; ++i) Hj[i] = hs[i] + hs[j + 1 + i];
+            const double hn = std::sqrt(hs[2 * (j + 1)]);
             Hj[j + 1] = hn;
             for (int i = 0; i < j; ++i) {
                 const double a = cs[i] * Hj[i] + sn[i] * Hj[i + 1];
@@ -712,11 +739,14 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
             gv[j + 1] = -sn[j] * gv[j];
             gv[j] = cs[j] * gv[j];
             est = std::fabs(gv[j + 1]);
-            if (kr->verbose > 1 || (kr->verbose && kr->iters % 100 == 0))
-                fprintf(stderr, "[sem gmres] it %d  |r| ~ %.6e\n", kr->iters, est);
+            ++done;
+            if (kr->verbose > 1 || (kr->verbose && (kr->iters + done) % 100 == 0))
+                fprintf(stderr, "[sem gmres] it %d  |r| ~ %.6e\n", kr->iters + done, est);
             if (!std::isfinite(est)) { set_error("gmres: non-finite residual"); return -3; }
-            if (est <= kr->atol || kr->iters >= kr->max_iters || !(hn > 0.0)) { ++j; break; }
+            if (est <= kr->atol || !(hn > 0.0)) stop = true;
         }
+        kr->iters += done;   // Arnoldi steps that enter the solution
+        const int j = done;
         // y = H^-1 g (back substitution on the rotated upper-triangular H), x += Pinv(V y)
         const int k = j;
         for (int i = k - 1; i >= 0; --i) {
