@@ -202,6 +202,9 @@ class ConvectionDiffusionSolver:
     def _get_interpol(self, f: np.ndarray, points_plot: typing.Tuple[np.ndarray, np.ndarray]) -> np.ndarray:
         """Interpolation of the global vector f at plotting points  (CD:180-188)."""
         d = self._dev
+        xs, ys = np.asarray(points_plot[0])[:, 0], np.asarray(points_plot[1])[0, :]     # ij-meshgrid, as SEM.py:262-263
+        if d.part is None:
+            return d.interpolate(d.to_device(f, self._buf[3]), xs, ys)
         f_e = d.scatter(d.to_device(f, self._buf[3])).cpu().numpy()
         return SEM.eval_interpolation(f_e, self.points_e, points_plot)
 

@@ -196,6 +196,35 @@ class NavierStokesSolver:
         self._solve_dev(self._out, self._x)
         return tuple(d.to_host(self._x[k]) for k in range(3))
 
+    def _get_update_inexact(self, dres_u, dres_v, dres_cont, rtol=1e-10, chunk=100, max_chunks=60):
+        """``_get_update`` for right-hand sides that need not lie in the range of the (singular) Jacobian --
+        the block-Jacobi preconditioner of a coupled Newton-Krylov driver hands over arbitrary Krylov vectors.  GMRES runs
+        in warm-started chunks and stops at the tolerance ``max(mtol sqrt(N), rtol |rhs|)`` or as soon as a chunk no longer
+        reduces the residual by 5 % (it has reached the part of the right-hand side outside the range: the least-squares
+        solution); it never raises.  Not part of the reference API."""
+        if not (self._have_sys and self._have_jac):
+            raise RuntimeError('NavierStokes: _get_residuals and _calc_jacobians must precede a linear solve')
+        d = self._dev
+        for k, a in enumerate((dres_u, dres_v, dres_cont)):
+            d.to_device(a, self._out[k])
+        self._x.zero_()
+        rhs_norm = float(np.sqrt(d.dot(self._out, self._out)))
+        prev = rhs_norm
+        for _ in range(max_chunks):
+            kr = self._krylov()
+            kr.atol = max(kr.atol, rtol * rhs_norm)
+            kr.max_iters = chunk
+            kr.restart = min(kr.restart, chunk)
+            st = self._state()
+            code = L.check(self._lib.sem_ns_solve(d.ctx, C.byref(st), self._out.data_ptr(), self._x.data_ptr(),
+                                                  C.byref(kr), self._work.data_ptr(), self._work.numel(), d.stream),
+                           "sem_ns_solve")
+            self.krylov_iters.append(kr.iters)
+            if code == 0 or not (kr.resnorm < 0.95 * prev):
+                break
+            prev = kr.resnorm
+        return tuple(d.to_host(self._x[k]) for k in range(3))
+
     def _get_solution(self, T, u0=None, v0=None, p0=None):
         """Newton iteration, device resident; updates u0, v0, p0 in place like NS:248-267 and returns them."""
         d = self._dev
@@ -238,6 +267,9 @@ class NavierStokesSolver:
     def _get_interpol(self, f, points_plot):
         """Interpolation of the global vector f at plotting points  (NS:280-288)."""
         d = self._dev
+        xs, ys = np.asarray(points_plot[0])[:, 0], np.asarray(points_plot[1])[0, :]     # ij-meshgrid, as SEM.py:262-263
+        if d.part is None:
+            return d.interpolate(d.to_device(f, self._in[3]), xs, ys)
         f_e = d.scatter(d.to_device(f, self._in[3])).cpu().numpy()
         return SEM.eval_interpolation(f_e, self.points_e, points_plot)
 

@@ -149,6 +149,20 @@ def global_convection_matrices(P, N_ex, N_ey, dx, dy):
     raise NotImplementedError("convection tensors are applied matrix-free: u@C_x = diag(u) G_x, C_x@T = diag(G_x T)")
 
 
+def interp_matrix_1d(P: int, N_e: int, h: float, pts: np.ndarray) -> np.ndarray:
+    """Dense 1-D interpolation matrix I[a, q] = l_q(pts[a]) onto arbitrary points from the N_e*P+1 global nodes of a line of
+    N_e elements of size h: the Lagrange basis of the element that holds the point (x2xi, SEM.py:23-36; evaluation matrix
+    GLL.py:105-116), zero elsewhere.  The SEM interpolant on an ij-meshgrid is then I_x F I_y^T (SEM.py:248-273)."""
+    pts = np.asarray(pts, dtype=np.float64).ravel()
+    e, xi = x2xi(pts, h)
+    e = np.clip(e, 0, N_e - 1)
+    S = GLL.standard_evaluation_matrix(P, xi)                    # [a, k]
+    I = np.zeros((pts.size, N_e * P + 1))
+    cols = e[:, None] * P + np.arange(P + 1)[None, :]
+    np.put_along_axis(I, cols, S, axis=1)
+    return I
+
+
 def eval_interpolation(u_e: np.ndarray, points_e: np.ndarray, points_plot: typing.Tuple[np.ndarray, np.ndarray]):
     """Evaluate the SEM interpolant of u_e[m,n,k,l] on an ij-meshgrid  (SEM.py:248-273).
 

@@ -9,13 +9,14 @@ import importlib
 
 from . import GLL  # noqa: F401
 
-__all__ = ["GLL", "SEM", "ConvectionDiffusionSolver", "NavierStokesSolver", "SemDevice"]
+__all__ = ["GLL", "SEM", "ConvectionDiffusionSolver", "NavierStokesSolver", "SemDevice", "Boussinesq_SequentialCoupler"]
 
 _LAZY = {
     "SEM": ("sem_b200.SEM", None),
     "SemDevice": ("sem_b200.device", "SemDevice"),
     "ConvectionDiffusionSolver": ("sem_b200.ConvectionDiffusion_Solver", "ConvectionDiffusionSolver"),
     "NavierStokesSolver": ("sem_b200.NavierStokes_Solver", "NavierStokesSolver"),
+    "Boussinesq_SequentialCoupler": ("sem_b200.Boussinesq_SequentialCoupler", None),
 }
 
 

@@ -761,14 +761,19 @@ inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_
     if (resident < 1) resident = 1;
     int Mx = Mx_req;
     if (Mx <= 0) {
-        // chunks of 16 element columns measured best at config 5 (9 resident rounds: 0.39 ms against 0.46 ms for 3 rounds of
-        // 49 columns); shorter chunks, down to 8, only when the mesh is too small to fill the device 4 times over
+        // A one-warp CTA marches its chunk in sequence (Mx steps + 1 priming step), and the CTAs run in resident rounds:
+        // time ~ ceil(CTAs / slots) * (Mx + 1) steps.  Large meshes: the cost is flat in Mx (16 and 12 columns both
+        // measured 0.37 ms at config 5; longer chunks re-read fewer halo lines, so ties go to the longer chunk).  Small
+        // slabs (8 GPUs on config 5: 120 interior columns) are quantised by the rounds: 6 columns cost 21 steps, 8
+        // columns 27.  Tiny meshes (the reference's own) end up with 2-column chunks: the launch is pure latency.
         const long long slots = (long long)sm_count * resident;
-        Mx = 16;
-        while (Mx > 8 && (long long)strips * ((m_hi - m_lo + Mx - 1) / Mx) < 4 * slots) Mx -= 4;
-        // less than one resident round even then (the reference's own meshes): the launch is pure latency, one warp
-        // marching Mx columns in sequence -- go down to 2 columns per warp
-        while (Mx > 2 && (long long)strips * ((m_hi - m_lo + Mx - 1) / Mx) < slots) Mx -= 2;
+        const int ncol = m_hi - m_lo;
+        long long best = -1;
+        for (int cand = 16; cand >= 2; --cand) {
+            const long long ctas = (long long)strips * ((ncol + cand - 1) / cand);
+            const long long cost = ((ctas + slots - 1) / slots) * (cand + 1);
+            if (best < 0 || cost * 100 < best * 98) { best = cost; Mx = cand; }   // a shorter chunk must win by > 2 %
+        }
     }
     if (Mx > m_hi - m_lo) Mx = m_hi - m_lo;
     q.Ty = EW;

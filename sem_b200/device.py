@@ -148,6 +148,17 @@ class SemDevice:
         L.check(self.lib.sem_d2h(self.ctx, vec.data_ptr(), out.ctypes.data, self.stream), "sem_d2h")
         return out
 
+    # ---- tensor-product interpolation (SEM.eval_interpolation, SEM.py:248-273; mesh-to-mesh transfer of the couplers) ------
+    def interpolate(self, vec, xs, ys):
+        """Values of the SEM interpolant of the device vector ``vec`` on the ij-meshgrid xs x ys: I_x F I_y^T with the 1-D
+        interpolation matrices of ``SEM.interp_matrix_1d``, two small dense products on the device.  Whole mesh only."""
+        from . import SEM
+        if self.part is not None and self.part.world > 1:
+            raise L.SemError("interpolation needs the whole mesh on one GPU")
+        Ix = torch.from_numpy(SEM.interp_matrix_1d(self.P, self.N_ex, self.dx, xs)).to(self.tdev)
+        Iy = torch.from_numpy(SEM.interp_matrix_1d(self.P, self.N_ey, self.dy, ys)).to(self.tdev)
+        return ((Ix @ vec[:, :self.NY]) @ Iy.T).cpu().numpy()
+
     # ---- fast-diagonalisation preconditioner ---------------------------------------------------------------------------
     def _fdm_1d(self, nel, h, dir_lo, dir_hi):
         """Generalised eigenpairs of the assembled 1-D pencil (K1, M1) of ``nel`` elements of size ``h`` (SEM.py:186-203

@@ -302,3 +302,41 @@ def test_fdm_preconditioner_matches_jacobi_and_is_mesh_independent(sem, bc):
             r = cd._get_residuals(T, u, v)
             assert np.linalg.norm(r) <= 1e-11 * np.sqrt(cd.N)
     assert max(its) <= 60 and its[-1] <= its[0] + 15
+
+
+@pytest.mark.parametrize("mode", ["GS", "JNK", "NJ"])
+def test_boussinesq_coupler_modes_reach_the_reference_fixed_point(sem, golden, mode):
+    """Native coupled driver (same ``run`` contract as OpenMDAO/Boussinesq_SequentialCoupler.py): all three strategies end
+    at the coupled state the reference's solvers reach (C3: P=4, 8x8, Re=1e3, Ra=1e3, Pr=0.71)."""
+    from sem_b200 import Boussinesq_SequentialCoupler as bsc
+    g = golden("boussinesq_c3")
+    Re, Ra, Pr = 1e3, 1e3, 0.71
+    cd = sem.ConvectionDiffusionSolver(1., 1., Re * Pr, 4, 8, 8, T_W=0.5, T_E=-0.5, mtol=1e-13)
+    ns = sem.NavierStokesSolver(1., 1., Re, Ra / Pr, 4, 8, 8, mtol=1e-13, mtol_newton=1e-13, iprint=[])
+    T, u, v, p, info = bsc.solve(cd, ns, mode=mode, mtol_nonlin=1e-11, mtol_gmres=1e-13)   # linear tol below nonlinear tol
+    assert relerr(T, g["T"]) < FIELD_TOL and relerr(u, g["u"]) < 1e-7 and relerr(v, g["v"]) < 1e-7
+    if mode == "GS":
+        assert info["nonlinear_its"] == int(g["sweeps"])
+
+
+def test_boussinesq_run_and_mesh_transfer(sem, golden):
+    """``run`` with the reference's signature; CD on a coarser mesh than NS (study/Boussinesq_run.py:50) exercises the
+    device tensor-product mesh-to-mesh transfer.  de Vahl Davis benchmark value u_max * Re * Pr = 3.649 at Ra = 1e3."""
+    from sem_b200 import Boussinesq_SequentialCoupler as bsc
+    g = golden("boussinesq_c3")
+    xp, yp = np.meshgrid(np.linspace(0, 1, 101), np.linspace(0, 1, 101), indexing='ij')
+    Tp, up, vp = bsc.run((xp, yp), 1., 1., mode='JNK')
+    assert abs(up.max() * 1e3 * 0.71 - float(g["umax_RePr"])) < 1e-5
+    Tp2, up2, vp2 = bsc.run((xp, yp), 1., 1., mode='GS', P_cd=4, N_ex_cd=4, N_ey_cd=4)
+    assert abs(up2.max() * 1e3 * 0.71 - 3.649) < 2e-2 and np.abs(Tp2 - Tp).max() < 1e-2
+
+
+def test_interpolation_device_matches_host(sem):
+    """SemDevice.interpolate (I_x F I_y^T on the device) against the host restatement of SEM.eval_interpolation."""
+    SEM = sem.SEM
+    cd = sem.ConvectionDiffusionSolver(1.3, 0.7, 1.0, 5, 6, 4)
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal(cd.N)
+    xp, yp = np.meshgrid(np.linspace(0, 1.3, 37), np.linspace(0, 0.7, 23), indexing='ij')
+    f_e = SEM.scatter(f, 5, 6, 4)
+    assert relerr(cd._get_interpol(f, (xp, yp)), SEM.eval_interpolation(f_e, cd.points_e, (xp, yp))) < 1e-13
