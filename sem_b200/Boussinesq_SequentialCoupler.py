@@ -204,3 +204,40 @@ def run(points_plot: typing.Tuple[np.ndarray, np.ndarray], L_x: float, L_y: floa
     T, u, v, p, _ = solve(cd, ns, mode=mode, mtol_nonlin=mtol_nonlin, AGi=AGi, AGr=AGr, AGc=AGc,
                           mtol_gmres=mtol_gmres, restart=restart)
     return cd._get_interpol(T, points_plot), ns._get_interpol(u, points_plot), ns._get_interpol(v, points_plot)
+
+
+def study_title(mode, Re, Ra, Pr, P, N_e, mtol_nonlin, AGi, AGr, AGc, mtol_gmres, restart, mtol_internal):
+    """File stem of a study run, as study/Boussinesq_run.py:35-43."""
+    title = f"Boussinesq{mode}_{Re:.1e}~{Ra:.1e}~{Pr}_{P}~{N_e}_"
+    if mode == 'GS':
+        return title + f"{mtol_nonlin:.0e}_{mtol_internal:.0e}"
+    if mode == 'NJ':
+        return title + f"{mtol_nonlin:.0e}~{AGi}~{AGr}~{AGc}_{mtol_internal:.0e}"
+    if mode == 'JNK':
+        return title + f"{mtol_nonlin:.0e}_{mtol_gmres:.0e}~{restart}_{mtol_internal:.0e}"
+    raise RuntimeError('Unknown method')
+
+
+def run_study(save=True, out_dir="Boussinesq_study", L_x=1., L_y=1., Re=1.e3, Ra=1.e3, Pr=0.71, P=4, N_e=8, mode='JNK',
+              mtol_nonlin=1e-10, AGi=8, AGr=0.8, AGc=0.2, mtol_gmres=1e-13, restart=20, mtol_internal=1e-13):
+    """One run of the parameter study (study/Boussinesq_run.py:26-135): CD on N_e/2 x N_e/2 elements, NS on N_e x N_e, and
+    the same output file -- ``np.savez`` with positional arrays ``arr_0..arr_3 = T_e, u_e, v_e, [iters_cd, iters_ns,
+    iter_nonlin]`` in the element layout ``[m, n, i, j]`` of ``SEM.scatter`` -- so the study's post-processing reads it
+    unchanged.  Returns (title, T_e, u_e, v_e, iters)."""
+    import os
+    from . import SEM
+    title = study_title(mode, Re, Ra, Pr, P, N_e, mtol_nonlin, AGi, AGr, AGc, mtol_gmres, restart, mtol_internal)
+    cd = ConvectionDiffusionSolver(L_x=L_x, L_y=L_y, Pe=Re * Pr, P=P, N_ex=int(N_e / 2), N_ey=int(N_e / 2),
+                                   T_W=0.5, T_E=-0.5, mtol=mtol_internal)
+    ns = NavierStokesSolver(L_x=L_x, L_y=L_y, Re=Re, Gr=Ra / Pr, P=P, N_ex=N_e, N_ey=N_e,
+                            mtol=mtol_internal, mtol_newton=mtol_internal, iprint=[])
+    T, u, v, p, info = solve(cd, ns, mode=mode, mtol_nonlin=mtol_nonlin, AGi=AGi, AGr=AGr, AGc=AGc,
+                             mtol_gmres=mtol_gmres, restart=restart)
+    T_e = SEM.scatter(T, cd._P, cd._N_ex, cd._N_ey)
+    u_e = SEM.scatter(u, ns._P, ns._N_ex, ns._N_ey)
+    v_e = SEM.scatter(v, ns._P, ns._N_ex, ns._N_ey)
+    iters = [info['iter_cd'], info['iter_ns'], info['nonlinear_its']]
+    if save:
+        os.makedirs(out_dir, exist_ok=True)
+        np.savez(os.path.join(out_dir, title), T_e, u_e, v_e, iters)
+    return title, T_e, u_e, v_e, iters

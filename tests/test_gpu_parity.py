@@ -340,3 +340,14 @@ def test_interpolation_device_matches_host(sem):
     xp, yp = np.meshgrid(np.linspace(0, 1.3, 37), np.linspace(0, 0.7, 23), indexing='ij')
     f_e = SEM.scatter(f, 5, 6, 4)
     assert relerr(cd._get_interpol(f, (xp, yp)), SEM.eval_interpolation(f_e, cd.points_e, (xp, yp))) < 1e-13
+
+
+def test_study_output_format(sem, tmp_path):
+    """study/Boussinesq_run.py output contract: title scheme and positional npz arrays in the [m, n, i, j] element layout."""
+    from sem_b200 import Boussinesq_SequentialCoupler as bsc
+    title, T_e, u_e, v_e, iters = bsc.run_study(out_dir=str(tmp_path), mode='GS', N_e=4, mtol_nonlin=1e-9)
+    assert title == "BoussinesqGS_1.0e+03~1.0e+03~0.71_4~4_1e-09_1e-13"
+    z = np.load(tmp_path / (title + ".npz"))
+    assert z.files == ["arr_0", "arr_1", "arr_2", "arr_3"]
+    assert z["arr_0"].shape == (2, 2, 5, 5) and z["arr_1"].shape == (4, 4, 5, 5) and z["arr_2"].shape == (4, 4, 5, 5)
+    assert list(z["arr_3"]) == iters and np.array_equal(z["arr_1"], u_e)
