@@ -57,9 +57,14 @@ struct sem_ctx {
     Comm comm;               // NCCL communicator of the element-column partition (has_comm)
     int has_comm;
     cudaStream_t s_side;     // low-priority stream: the interior of an operator runs here while the interface lines travel
+    cudaStream_t s_side2;    // second side stream: right edge and interior run concurrently on small slabs
     cudaEvent_t ev_in, ev_edge, ev_side;
     // host-buffer pipeline (sem_cd_jvp_host): upload / download streams, second staging buffer, per-segment events
     cudaStream_t s_h2d, s_d2h;
+    cudaStream_t s_main;     // partitioned applies run (and are captured) here, ordered against the caller's stream by events
+    cudaEvent_t ev_g0, ev_g1;
+    struct GraphEntry { unsigned char key[sizeof(MarchArgs) + 8 * sizeof(double*) + 16]; int uses; cudaGraphExec_t exec; } gcache[8];
+    int gcache_next;
     cudaStream_t s_solve;    // the Krylov solvers run here: CUDA graphs cannot be captured on the legacy default stream
     double* dStageOut;
     cudaEvent_t ev_up[SEM_HOST_SEGMENTS], ev_done[SEM_HOST_SEGMENTS], ev_start, ev_end;
@@ -154,12 +159,15 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     cudaFree(c->dD); cudaFree(c->dKs); cudaFree(c->dw);
     if (c->dKdiag) cudaFree(c->dKdiag);
     if (c->dStage) cudaFree(c->dStage);
+    for (auto& e : c->gcache)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
     if (c->has_comm) comm_destroy(c->comm);
     if (c->dStageOut) cudaFree(c->dStageOut);
     if (c->fQx) { cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2); }
     if (c->blas) { cublasDestroy(c->blas); cudaFree(c->blas_ws); }
     if (c->streams_ready) {
-        cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_solve);
+        cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_side2); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_solve); cudaStreamDestroy(c->s_main);
+        cudaEventDestroy(c->ev_g0); cudaEventDestroy(c->ev_g1);
         cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_side); cudaEventDestroy(c->ev_edge); cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_end);
         for (int i = 0; i < SEM_HOST_SEGMENTS; ++i) { cudaEventDestroy(c->ev_up[i]); cudaEventDestroy(c->ev_done[i]); }
     }
@@ -273,9 +281,13 @@ static int ensure_streams(sem_ctx* c) {
     int lo = 0, hi = 0;
     SEM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority
     SEM_CUDA(cudaStreamCreateWithPriority(&c->s_side, cudaStreamNonBlocking, lo));
+    SEM_CUDA(cudaStreamCreateWithPriority(&c->s_side2, cudaStreamNonBlocking, hi));
     SEM_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     SEM_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     SEM_CUDA(cudaStreamCreateWithFlags(&c->s_solve, cudaStreamNonBlocking));
+    SEM_CUDA(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_g0, cudaEventDisableTiming));
+    SEM_CUDA(cudaEventCreateWithFlags(&c->ev_g1, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
     SEM_CUDA(cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming));
@@ -297,11 +309,46 @@ static int ensure_streams(sem_ctx* c) {
 // transfer (interface lines final) and again after the interior (interior lines final).
 static const int SEM_EDGE_COLUMNS = 4;   // a launch this narrow is pure latency (one warp per strip, 4 marching steps)
 
+typedef std::function<int(cudaStream_t)> postop;
+
+// the partitioned sequence itself, everything ordered on `st` (and the side stream forked from / joined to it)
+static int partitioned_apply(sem_ctx* c, int mode, MarchArgs& A, double* const* f, int n, int el, int er, cudaStream_t st,
+                             const postop& post) {
+    const int nex = c->g.nex;
+    SEM_CUDA(cudaEventRecord(c->ev_in, st));                 // inputs are ready here
+    SEM_CUDA(cudaStreamWaitEvent(c->s_side, c->ev_in, 0));
+    // A large interior (several resident rounds of one-warp CTAs) goes first: it starts at once, and the edge launches on
+    // the higher-priority stream slip in as soon as its first CTAs retire -- long before it ends.  A small interior
+    // (8 GPUs on config 5: about one round) would delay the edges past its own end, so there the edges go first.
+    const long long interior_ctas = (long long)(c->g.ney / 8 + 1) * ((nex - el - er + 15) / 16);
+    const bool interior_first = interior_ctas >= 3ll * 6 * c->sm_count;
+    if (interior_first) {
+        if (march(c, mode, A, c->s_side, el, nex - er)) return -1;
+        SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
+        if (march(c, mode, A, st, 0, el)) return -1;
+        if (march(c, mode, A, st, nex - er, nex)) return -1;
+    } else {
+        // three concurrent launches, the edges submitted first so that their CTAs are placed first
+        SEM_CUDA(cudaStreamWaitEvent(c->s_side2, c->ev_in, 0));
+        if (march(c, mode, A, st, 0, el)) return -1;                   // left edge
+        if (march(c, mode, A, c->s_side2, nex - er, nex)) return -1;   // right edge
+        SEM_CUDA(cudaEventRecord(c->ev_edge, c->s_side2));
+        if (march(c, mode, A, c->s_side, el, nex - er)) return -1;     // interior (low priority)
+        SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
+        SEM_CUDA(cudaStreamWaitEvent(st, c->ev_edge, 0));
+    }
+    if (post && post(st)) return -1;
+    if (comm_exchange_transfer(c->comm, c->g, f, n, st)) return -1;
+    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
+    if (post && post(st)) return -1;
+    return comm_exchange_finish(c->comm, c->g, f, n, st);
+}
+
 static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializer_list<double*> fields, cudaStream_t st,
-                              const std::function<int()>& post = nullptr) {
+                              const postop& post = nullptr) {
     if (!c->has_comm) {
         if (march(c, mode, A, st)) return -1;
-        return post ? post() : 0;
+        return post ? post(st) : 0;
     }
     double* f[8];
     int n = 0;
@@ -312,35 +359,60 @@ static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializ
     const int er = c->g.has_right ? std::min(SEM_EDGE_COLUMNS, nex - el) : 0;
     if (el + er >= nex || n == 0) {   // nothing left to overlap with
         if (march(c, mode, A, st)) return -1;
-        if (post && post()) return -1;
+        if (post && post(st)) return -1;
         return n ? comm_exchange_add(c->comm, c->g, f, n, st) : 0;
     }
     if (ensure_streams(c)) return -1;
-    SEM_CUDA(cudaEventRecord(c->ev_in, st));                 // inputs are ready here
-    SEM_CUDA(cudaStreamWaitEvent(c->s_side, c->ev_in, 0));
-    // A large interior (several resident rounds of one-warp CTAs) goes first: it starts at once, and the edge launches on
-    // the higher-priority caller's stream slip in as soon as its first CTAs retire -- long before it ends.  A small interior
-    // (8 GPUs on config 5: about one round) would delay the edges past its own end, so there the edges go first.
-    const long long interior_ctas = (long long)(c->g.ney / 8 + 1) * ((nex - el - er + 15) / 16);
-    const bool interior_first = interior_ctas >= 3ll * 6 * c->sm_count;
-    if (interior_first) {
-        if (march(c, mode, A, c->s_side, el, nex - er)) return -1;
-        SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
-        if (march(c, mode, A, st, 0, el)) return -1;
-        if (march(c, mode, A, st, nex - er, nex)) return -1;
-    } else {
-        if (march(c, mode, A, st, 0, el)) return -1;             // left edge on the caller's stream ...
-        if (march(c, mode, A, c->s_side, nex - er, nex)) return -1;   // ... right edge concurrently on the side stream
-        SEM_CUDA(cudaEventRecord(c->ev_edge, c->s_side));
-        if (march(c, mode, A, c->s_side, el, nex - er)) return -1;    // interior behind it
-        SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
-        SEM_CUDA(cudaStreamWaitEvent(st, c->ev_edge, 0));
+    static const bool no_graph = std::getenv("SEM_B200_NO_GRAPH") != nullptr;
+    if (no_graph) return partitioned_apply(c, mode, A, f, n, el, er, st, post);
+
+    // The sequence is ~12 host calls (3 launches, 6 event operations, a grouped NCCL send/recv, the add): at 8 GPUs the
+    // host's enqueue time exceeds the device time of the apply.  The second time the same apply (mode, arguments, fields)
+    // comes along it is captured -- NCCL operations included, every rank captures in lock step -- and from then on it is
+    // replayed with one cudaGraphLaunch.  Capture is not allowed on the legacy default stream a caller may hand in, so the
+    // partitioned applies run on a context-owned stream ordered against the caller's by two events.
+    A.zero = 0;
+    unsigned char key[sizeof(c->gcache[0].key)];
+    std::memset(key, 0, sizeof(key));
+    std::memcpy(key, &A, sizeof(A));
+    std::memcpy(key + sizeof(A), f, sizeof(double*) * n);
+    const int tail[4] = {mode, n, c->Mx_req, c->Ty_req};
+    std::memcpy(key + sizeof(A) + 8 * sizeof(double*), tail, sizeof(tail));
+    sem_ctx::GraphEntry* e = nullptr;
+    for (auto& g : c->gcache)
+        if (g.uses > 0 && std::memcmp(g.key, key, sizeof(key)) == 0) e = &g;
+    cudaStream_t sm = c->s_main;
+    SEM_CUDA(cudaEventRecord(c->ev_g0, st));
+    SEM_CUDA(cudaStreamWaitEvent(sm, c->ev_g0, 0));
+    int rc = 0;
+    if (e && e->exec) {
+        SEM_CUDA(cudaGraphLaunch(e->exec, sm));
+    } else if (!e) {                      // first sighting: run eagerly (also establishes the NCCL connections)
+        e = &c->gcache[c->gcache_next];
+        c->gcache_next = (c->gcache_next + 1) % 8;
+        if (e->exec) cudaGraphExecDestroy(e->exec);
+        e->exec = nullptr;
+        std::memcpy(e->key, key, sizeof(key));
+        e->uses = 1;
+        rc = partitioned_apply(c, mode, A, f, n, el, er, sm, post);
+    } else {                              // second sighting: capture, instantiate, launch
+        e->uses++;
+        cudaGraph_t graph = nullptr;
+        SEM_CUDA(cudaStreamBeginCapture(sm, cudaStreamCaptureModeThreadLocal));
+        rc = partitioned_apply(c, mode, A, f, n, el, er, sm, post);
+        const cudaError_t ce = cudaStreamEndCapture(sm, &graph);
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            set_error(std::string("apply_and_exchange: graph capture failed: ") + cudaGetErrorString(ce));
+            return -1;
+        }
+        SEM_CUDA(cudaGraphInstantiate(&e->exec, graph, 0));
+        cudaGraphDestroy(graph);
+        SEM_CUDA(cudaGraphLaunch(e->exec, sm));
     }
-    if (post && post()) return -1;
-    if (comm_exchange_transfer(c->comm, c->g, f, n, st)) return -1;
-    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
-    if (post && post()) return -1;
-    return comm_exchange_finish(c->comm, c->g, f, n, st);
+    SEM_CUDA(cudaEventRecord(c->ev_g1, sm));
+    SEM_CUDA(cudaStreamWaitEvent(st, c->ev_g1, 0));
+    return rc;
 }
 
 static MarchArgs zero_args() {
@@ -498,8 +570,8 @@ extern "C" int sem_ns_residual(sem_ctx* c, const sem_ns_state* s, const double* 
     A.y0 = ru; A.y1 = rv; A.y2 = rc;
     fill_ns_bc(c, A.bc, s->bc, 1);
     // NS:116-119: pin first, then the Neumann rows (they win if the pin sits on the boundary)
-    return apply_and_exchange(c, MODE_NS, A, {ru, rv, rc}, (cudaStream_t)stream, [&]() {
-        return aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_NS, A, {ru, rv, rc}, (cudaStream_t)stream, [&](cudaStream_t s) {
+        return aux_neumann_rows(c->g, c->tab(), p, rc, c->pin_gx, c->pin_iy, 0, s);
     });
 }
 
@@ -521,8 +593,8 @@ extern "C" int sem_ns_jvp(sem_ctx* c, const sem_ns_state* s, const double* du, c
     A.y0 = ou; A.y1 = ov; A.y2 = oc;
     fill_ns_bc(c, A.bc, s->bc, 0);
     // NS:157-158: Neumann rows first, then the pin (the pin wins)
-    return apply_and_exchange(c, MODE_NS, A, {ou, ov, oc}, (cudaStream_t)stream, [&]() {
-        return aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, (cudaStream_t)stream);
+    return apply_and_exchange(c, MODE_NS, A, {ou, ov, oc}, (cudaStream_t)stream, [&](cudaStream_t s) {
+        return aux_neumann_rows(c->g, c->tab(), dp, oc, c->pin_gx, c->pin_iy, 1, s);
     });
 }
 

@@ -130,3 +130,33 @@ def test_boussinesq_fixed_point_residual(golden):
     r = np.hstack((cd._get_residuals(g["T"], g["u"], g["v"]),) + ns._get_residuals(g["u"], g["v"], g["p"], g["T"]))
     assert np.linalg.norm(r) < 1e-9 * np.sqrt(r.size)
     assert abs(float(g["umax_RePr"]) - 3.649) < 5e-3 and abs(float(g["vmax_RePr"]) - 3.697) < 1e-2
+
+
+def test_boussinesq_coupler_logic_on_the_oracle_solvers():
+    """The native coupled driver (sem_b200/Boussinesq_SequentialCoupler.py) only talks to its two solvers through the
+    reference's method names, so its host logic can be exercised on the CPU with the oracle classes: block Gauss-Seidel
+    and Jacobian-free Newton-Krylov reach the same coupled state (the C3 physics on P = 4, 4 x 4 elements)."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sem_b200", "Boussinesq_SequentialCoupler.py")
+    src = open(path).read()
+    # the module imports the GPU classes only for type annotations and for run(): strip them for the CPU check
+    src = src.replace("from .ConvectionDiffusion_Solver import ConvectionDiffusionSolver\n", "ConvectionDiffusionSolver = object\n")
+    src = src.replace("from .NavierStokes_Solver import NavierStokesSolver\n", "NavierStokesSolver = object\n")
+    mod = types.ModuleType("bsc_host")
+    exec(compile(src, path, "exec"), mod.__dict__)
+    Re, Ra, Pr = 1e3, 1e3, 0.71
+    out = {}
+    for mode in ("GS", "JNK"):
+        cd = so.CDOracle(1., 1., Re * Pr, 4, 4, 4, T_W=0.5, T_E=-0.5, mtol=1e-13)
+        ns = so.NSOracle(1., 1., Re, Ra / Pr, 4, 4, 4, mtol=1e-13, mtol_newton=1e-13)
+        for s in (cd, ns):
+            s._P, s._N_ex, s._N_ey = 4, 4, 4
+        out[mode] = mod.solve(cd, ns, mode=mode, mtol_nonlin=1e-11, mtol_gmres=1e-13, maxiter=40)
+    for a, b in zip(out["GS"][:3], out["JNK"][:3]):
+        assert np.linalg.norm(a - b) <= 1e-8 * max(np.linalg.norm(b), 1e-30)
+    assert out["JNK"][4]["nonlinear_its"] < out["GS"][4]["nonlinear_its"]
+    assert mod.study_title('JNK', 1e3, 1e3, 0.71, 4, 8, 1e-10, 8, 0.8, 0.2, 1e-13, 20, 1e-13) == \
+        "BoussinesqJNK_1.0e+03~1.0e+03~0.71_4~8_1e-10_1e-13~20_1e-13"
