@@ -247,8 +247,8 @@ extern "C" int sem_d2h(sem_ctx* c, const double* vec, double* host, void* stream
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Kernel generation: v3 (one warp per strip, TMA-staged, folded tables) for even orders; v1 for odd orders.
-// SEM_B200_MARCH=1 forces v1 everywhere (A/B comparisons only).
+// Kernel generation: v3 (one warp per strip, TMA-staged, folded tables) for every order.  SEM_B200_MARCH=1 selects the
+// round-1 v1 kernel (one column per thread, CTA barriers) for A/B comparisons.
 static int march_generation() {
     static const int v = [] {
         const char* e = std::getenv("SEM_B200_MARCH");
@@ -264,7 +264,7 @@ static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st, int m_lo =
     if (m_lo >= m_hi) return 0;
     const auto& ord = g_orders[c->g.P - 1];
     const int gen = march_generation();
-    if (gen == 3 && c->g.P % 2 == 0) {
+    if (gen == 3) {
         const MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm, m_lo, m_hi);
         return ord.launch3(mode, c->g, A, q, st);
     }

@@ -32,37 +32,41 @@
 
 #include <type_traits>
 
-#ifndef SEM_V3_CONV
-#define SEM_V3_CONV 0   // A/B switch. bit 0: y phase, bit 1: x phase run convergent (all lanes compute, stores guarded).
-                        // Measured at config 5 (B200): 0 is fastest for CD (0.39 ms vs 0.48-0.50) and NS; K is indifferent.
-#endif
-
 namespace semb {
 
-// Folded 1-D tables of order P (P even), rows i = 0 .. P/2.  Row layout (doubles):
-//   pairs k = 0 .. H   : ( Ke[i][k], De[i][k] )     Ke = (Ks[i][k] + Ks[i][P-k]) / 2   (k = H: Ks[i][H]),  same for De from wD
-//   pairs k = 0 .. H-1 : ( Ko[i][k], Do[i][k] )     Ko = (Ks[i][k] - Ks[i][P-k]) / 2
+// Folded 1-D tables of order P.  With n = P + 1 nodes: HE = ceil(n/2) even-part entries, HO = floor(n/2) odd-part entries;
+// rows i = 0 .. HE-1, row i paired with row P-i (an even order has the unpaired middle row H = P/2).  Row layout (doubles):
+//   pairs k = 0 .. HE-1 : ( Ke[i][k], De[i][k] )     Ke = (Ks[i][k] + Ks[i][P-k]) / 2   (middle column: Ks[i][H]),  same for De from wD
+//   pairs k = 0 .. HO-1 : ( Ko[i][k], Do[i][k] )     Ko = (Ks[i][k] - Ks[i][P-k]) / 2
 // with wD[i][k] = w_i D[i][k] (GLL.py:30,45-59,73-81).
 template <int P>
 struct __align__(16) Tab3 {
-    static constexpr int H = P / 2;
+    static constexpr int HE = (P + 2) / 2, HO = (P + 1) / 2;
     static constexpr int RS = 2 * (P + 1);
-    double T[(H + 1) * RS];
+    double T[HE * RS];
 };
 template <int P>
 __constant__ Tab3<P> c_tab3;
 
-// NC node columns per lane in the x phase, NL node lines per lane in the y phase (NL >= NC)
-template <int MODE> struct March3Traits { static constexpr int NC = 2, NL = 2; };
-template <> struct March3Traits<MODE_NS> { static constexpr int NC = 1, NL = 1; };
+// NC node columns per lane in the x phase, NL node lines per lane in the y phase (NL >= NC).  Two per lane (16-byte shared
+// and global accesses, one table fetch per four DFMAs) for the one- and two-field modes at even orders up to 10; one per
+// lane for NS (three contracted fields), for odd orders (an odd element width breaks the 16-byte alignment of the line
+// pairs) and for orders >= 12 (the unrolled two-column code no longer fits the register file).
+template <int P, int MODE>
+struct March3Traits {
+    static constexpr bool WIDE = (MODE != MODE_NS) && (P % 2 == 0) && (P <= 10);
+    static constexpr int NC = WIDE ? 2 : 1, NL = WIDE ? 2 : 1;
+};
 
 // compile-time geometry of a warp strip
 template <int P, int MODE>
 struct March3Geom {
     using TR = ModeTraits<MODE>;
-    static constexpr int NC = March3Traits<MODE>::NC, NL = March3Traits<MODE>::NL;
+    static constexpr int NC = March3Traits<P, MODE>::NC, NL = March3Traits<P, MODE>::NL;
     static constexpr int EW = (32 * NC / P) > 0 ? (32 * NC / P) : 1;     // element rows per strip
-    static constexpr int NCOLP = (P + EW * P + 1 + 1) & ~1;              // staged columns: halo + own + top node, even
+    // staged columns: halo (P, or P + 1 when the strip starts at an odd node so that the TMA source stays 16-byte
+    // aligned) + own + top node, rounded up to an even count
+    static constexpr int NCOLP = (P + (P % 2) + EW * P + 1 + 1) & ~1;
     // Row pitch (doubles).  The x phase reads consecutive columns (any pitch is conflict free).  In the y phase 8
     // consecutive lanes -- G = P/NL line slots of 8/G elements -- read 16-byte units at slot*(PITCH/2) + element*(P/2):
     // PITCH/2 == 1 (mod 8) makes that the lane number for every P; when P is a power of two any ODD PITCH/2 gives 8
@@ -73,7 +77,6 @@ struct March3Geom {
     static constexpr int NSTG = TR::NF + 2 * TR::NV;                     // staged fields: contracted, then U, then V
     static constexpr int SMEM_DOUBLES = (2 * NSTG + TR::NACC) * P * PITCH + TR::NACC * P * TPW;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 16;
-    static_assert(P % 2 == 0, "v3 needs an even polynomial order");
     static_assert(EW * P / NC <= 32 && (P / NL) * EW <= 32, "a strip must fit one warp in both phases");
 };
 
@@ -105,7 +108,9 @@ template <int P, int MODE, bool PW>
 struct March3 {
     using MM = March<P, MODE>;
     using GE = March3Geom<P, MODE>;
-    static constexpr int n = P + 1, H = P / 2;
+    static constexpr int n = P + 1, HE = Tab3<P>::HE, HO = Tab3<P>::HO;
+    static constexpr bool MID = (P % 2 == 0);                 // even order: row / column P/2 has no partner
+    static __host__ __device__ constexpr bool has_partner(int I) { return !(MID && I == HE - 1); }
     static constexpr int NF = MM::NF, NV = MM::NV, NACC = MM::NACC, NOUT = MM::NOUT;
     static constexpr int NC = GE::NC, NL = GE::NL, EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, NSTG = GE::NSTG;
     static constexpr int G = P / NL;   // lanes per element in the y phase
@@ -114,9 +119,9 @@ struct March3 {
     static constexpr int NPD = NODE_FAST ? 4 : 1;                // pointwise diagonals prefetched into registers per node
 
     // ---- folded contraction: rows I and P-I of (Ks a) and (wD a) for NV_ vectors at once --------------------------------
-    // sK[0] / sD[0]: row I, sK[1] / sD[1]: row P-I (I < H only).  DIR 0: x phase, 1: y phase (selects the fields needed).
+    // sK[0] / sD[0]: row I, sK[1] / sD[1]: row P-I (when row I has a partner).  DIR 0: x phase, 1: y phase (selects the fields needed).
     template <int I, int DIR, int NV_>
-    static __device__ __forceinline__ void contract(const double (&e)[NV_][NF][H + 1], const double (&o)[NV_][NF][H],
+    static __device__ __forceinline__ void contract(const double (&e)[NV_][NF][HE], const double (&o)[NV_][NF][HO],
                                                     double (&sK)[2][NV_][NF], double (&sD)[2][NV_][NF], int z) {
         // z: always 0, but uniform and loop-variant (see the kernel) -- keeps the table fetches just-in-time LDCUs
         const double2* __restrict__ t2 = reinterpret_cast<const double2*>(
@@ -126,27 +131,28 @@ struct March3 {
         for (int v = 0; v < NV_; ++v)
 #pragma unroll
             for (int f = 0; f < NF; ++f) EK[v][f] = ED[v][f] = OK[v][f] = OD[v][f] = 0.0;
+        constexpr bool PAIRED = has_partner(I);   // the middle row of an even order: De and Ko rows are zero
 #pragma unroll
-        for (int k = 0; k <= H; ++k) {
+        for (int k = 0; k < HE; ++k) {
             const double2 c = t2[k];
 #pragma unroll
             for (int v = 0; v < NV_; ++v)
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     const bool nk = DIR == 0 ? MM::x_needs_K(f) : MM::y_needs_K(f);
-                    const bool nd = (DIR == 0 ? MM::x_needs_D(f) : MM::y_needs_D(f)) && I < H;   // De row H is zero
+                    const bool nd = (DIR == 0 ? MM::x_needs_D(f) : MM::y_needs_D(f)) && PAIRED;
                     if (nk) EK[v][f] = (k == 0) ? c.x * e[v][f][0] : fma(c.x, e[v][f][k], EK[v][f]);
                     if (nd) ED[v][f] = (k == 0) ? c.y * e[v][f][0] : fma(c.y, e[v][f][k], ED[v][f]);
                 }
         }
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-            const double2 c = t2[H + 1 + k];
+        for (int k = 0; k < HO; ++k) {
+            const double2 c = t2[HE + k];
 #pragma unroll
             for (int v = 0; v < NV_; ++v)
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    const bool nk = (DIR == 0 ? MM::x_needs_K(f) : MM::y_needs_K(f)) && I < H;   // Ko row H is zero
+                    const bool nk = (DIR == 0 ? MM::x_needs_K(f) : MM::y_needs_K(f)) && PAIRED;
                     const bool nd = DIR == 0 ? MM::x_needs_D(f) : MM::y_needs_D(f);
                     if (nk) OK[v][f] = (k == 0) ? c.x * o[v][f][0] : fma(c.x, o[v][f][k], OK[v][f]);
                     if (nd) OD[v][f] = (k == 0) ? c.y * o[v][f][0] : fma(c.y, o[v][f][k], OD[v][f]);
@@ -164,13 +170,13 @@ struct March3 {
     }
 
     // fold an element line a[0..P] into its even / odd parts
-    static __device__ __forceinline__ void fold(const double (&a)[n], double (&e)[H + 1], double (&o)[H]) {
+    static __device__ __forceinline__ void fold(const double (&a)[n], double (&e)[HE], double (&o)[HO]) {
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
+        for (int k = 0; k < HO; ++k) {
             e[k] = a[k] + a[P - k];
             o[k] = a[k] - a[P - k];
         }
-        e[H] = a[H];
+        if constexpr (MID) e[HO] = a[HO];
     }
 
     // ---- per-node combination of the contractions (sD already carries the quadrature weight of its own direction) -------
@@ -225,27 +231,34 @@ struct March3 {
             cky[l] = wx[l] * ky;
             ccw[l] = cc * wx[l];
         }
-        double e[NL][NF][H + 1], o[NL][NF][H];
+        constexpr bool V2 = (P % 2 == 0);   // even order: col0 is even, 16-byte shared accesses
+        double e[NL][NF][HE], o[NL][NF][HO];
 #pragma unroll
         for (int l = 0; l < NL; ++l)
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const double* row = sB + (f * P + sp + l * G) * PITCH + col0;
                 double a[n];
+                if constexpr (V2) {
 #pragma unroll
-                for (int k = 0; k < P; k += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(row + k);
-                    a[k] = v.x;
-                    a[k + 1] = v.y;
+                    for (int k = 0; k < P; k += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(row + k);
+                        a[k] = v.x;
+                        a[k + 1] = v.y;
+                    }
+                    a[P] = row[P];
+                } else {
+#pragma unroll
+                    for (int k = 0; k <= P; ++k) a[k] = row[k];
                 }
-                a[P] = row[P];
                 fold(a, e[l][f], o[l][f]);
             }
         const double* sV = sB + ((NF + 1) * P + sp) * PITCH + col0;   // V line of slot sp (NV modes)
         if constexpr (FULLROWS) {
             double Y[NL][NACC][n];
-            static_for<0, H + 1>([&](auto Jc) {
+            static_for<0, HE>([&](auto Jc) {
                 constexpr int J = decltype(Jc)::value;
+                constexpr bool PAIRED = has_partner(J);
                 double sK[2][NL][NF], sD[2][NL][NF];
                 contract<J, 1, NL>(e, o, sK, sD, z);
 #pragma unroll
@@ -253,13 +266,13 @@ struct March3 {
                     double Vlo = 0.0, Vhi = 0.0;
                     if constexpr (NV) {
                         Vlo = sV[l * G * PITCH + J];
-                        if constexpr (J < H) Vhi = sV[l * G * PITCH + P - J];
+                        if constexpr (PAIRED) Vhi = sV[l * G * PITCH + P - J];
                     }
                     double y[NACC];
                     ycomb(sK[0][l], sD[0][l], Vlo, cky[l], wx[l], ccw[l], y);
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) Y[l][a][J] = y[a];
-                    if constexpr (J < H) {
+                    if constexpr (PAIRED) {
                         ycomb(sK[1][l], sD[1][l], Vhi, cky[l], wx[l], ccw[l], y);
 #pragma unroll
                         for (int a = 0; a < NACC; ++a) Y[l][a][P - J] = y[a];
@@ -272,9 +285,14 @@ struct March3 {
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) {
                         double* dst = sA + (a * P + sp + l * G) * PITCH + col0;
+                        if constexpr (V2) {
 #pragma unroll
-                        for (int j = 0; j < P; j += 2)
-                            *reinterpret_cast<double2*>(dst + j) = make_double2(Y[l][a][j], Y[l][a][j + 1]);
+                            for (int j = 0; j < P; j += 2)
+                                *reinterpret_cast<double2*>(dst + j) = make_double2(Y[l][a][j], Y[l][a][j + 1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < P; ++j) dst[j] = Y[l][a][j];
+                        }
                         sT[(a * P + sp + l * G) * TPW + topslot] = Y[l][a][P];
                     }
             }
@@ -297,21 +315,18 @@ struct March3 {
 
     // ---- y phase over the P staged lines of one buffer ----------------------------------------------------------------------
     // main pass: lane q < G*nty contracts NL lines of element q / G (slots q % G, ..); halo pass: lanes q < G evaluate the
-    // top row of the element below the strip (its node j = 0 is tile column 0) -> sT[line][0].  wx: x-weights of the
+    // top row of the element below the strip (its node j = 0 is tile column halo - P) -> sT[line][0].  wx: x-weights of the
     // slots (lane % G) + l*G -- the same for both passes because q < G implies q % G == q.
     static __device__ __forceinline__ void yphase(int nty, int halo, const double (&wx)[NL], double cc, double ky,
                                                   const double* __restrict__ sB, double* __restrict__ sA,
                                                   double* __restrict__ sT, int z) {
         const int q = threadIdx.x;
         const int sp = q % G;
-        const int nn = (q / G < EW) ? q / G : EW - 1;   // lanes beyond the strip recompute the last element (no stores)
-#if SEM_V3_CONV & 1
-        yitem<true>(q < G * nty, sp, halo + nn * P, nn + 1, wx, cc, ky, sB, sA, sT, z);
-        if (halo > 0) yitem<false>(q < G, sp, 0, 0, wx, cc, ky, sB, sA, sT, z);
-#else
+        const int nn = q / G;
+        // Divergent on purpose: running both passes with all lanes and guarded stores measured slower (CD 0.48 ms against
+        // 0.39 ms at config 5: the convergent code spills uniform registers, R2UR.FILL).
         if (q < G * nty) yitem<true>(true, sp, halo + nn * P, nn + 1, wx, cc, ky, sB, sA, sT, z);
-        if (halo > 0 && q < G) yitem<false>(true, sp, 0, 0, wx, cc, ky, sB, sA, sT, z);
-#endif
+        if (halo > 0 && q < G) yitem<false>(true, sp, halo - P, 0, wx, cc, ky, sB, sA, sT, z);
     }
 
     // store the NOUT outputs of the lane's NC nodes of line ix
@@ -418,7 +433,7 @@ struct March3 {
             ckx[c] = wyA[c] * (2.0 / g.dx);
             ccw[c] = cc * wyA[c];
         }
-        double e[NC][NF][H + 1], o[NC][NF][H];
+        double e[NC][NF][HE], o[NC][NF][HO];
         double aprev[NC][NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
@@ -473,7 +488,7 @@ struct March3 {
             }
         };
 
-        static_for<0, (FULL ? H + 1 : 1)>([&](auto Ic) {
+        static_for<0, (FULL ? HE : 1)>([&](auto Ic) {
             constexpr int I = decltype(Ic)::value;
             double sK[2][NC][NF], sD[2][NC][NF];
             contract<I, 0, NC>(e, o, sK, sD, z);
@@ -504,7 +519,7 @@ struct March3 {
                 }
                 finalize_fast(g, A, ix, iy0, own, xp, yp, node, wyA, pd[I]);
             }
-            if constexpr (I < H) {   // row P - I
+            if constexpr (has_partner(I)) {   // row P - I
                 constexpr int R = P - I;
                 double Uc[NC], xp[NC][NOUT];
                 load_U(R, Uc);
@@ -555,7 +570,9 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     const bool last_strip = (blockIdx.x == gridDim.x - 1);
     const int m0 = m_lo + blockIdx.y * Mx;              // the launch covers the element columns m_lo .. m_hi - 1
     const int m1 = min(m0 + Mx, m_hi);
-    const int halo = (n0 > 0) ? P : 0;
+    // y-halo: the P nodes below the strip, one more when the strip starts at an odd node (odd orders) so that the TMA
+    // source address stays 16-byte aligned
+    const int halo = (n0 > 0) ? P + ((n0 * P - P) & 1) : 0;
     const int ybase = n0 * P - halo;                      // even
     const int ncolp = (halo + nty * P + 1 + 1) & ~1;      // staged columns per line (even)
     const int nown = nty * P + (last_strip ? 1 : 0);      // the strip owns tile columns halo .. halo + nown - 1
@@ -723,11 +740,7 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         const int z = m >> 30;
         M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, z);
         __syncwarp();
-#if SEM_V3_CONV & 2
-        M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
-#else
         if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
-#endif
         __syncwarp();   // buffer b and the accumulators are free: refill the buffer with the lines of step m + 2
         if (m + 2 < m1) issue(b, (m + 2) * P + 1, P, 0);
     }
@@ -736,25 +749,16 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     if (xthr && m1 == g.nex) M3::finalize_slow(g, A, g.nex * P, iy0, own, xc, yc, a0, wyA);
 }
 
-// host mirror of the compile-time geometry
-struct March3Shape { int nc, nl, nstg, nacc; };
-inline March3Shape march3_shape(int mode) {
-    switch (mode) {
-        case MODE_K: return {2, 2, 1, 1};
-        case MODE_G: return {2, 2, 1, 1};
-        case MODE_DIV: return {2, 2, 2, 1};
-        case MODE_CD: return {2, 2, 3, 1};
-        default: return {1, 1, 5, 3};
-    }
-}
+// host mirror of March3Traits: node columns per lane of a (P, mode)
+inline int march3_nc(int P, int mode) { return (mode != MODE_NS && P % 2 == 0 && P <= 10) ? 2 : 1; }
 
 // grid: x = strips of EW element rows (+ the last strip with the remainder and the topmost node column), y = chunks of Mx
 // element columns (the x-halo costs 1/Mx extra reads and one extra y phase per chunk).
 inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_count, size_t smem_bytes, size_t smem_sm,
                                  int m_lo, int m_hi) {
     MarchGeom q;
-    const March3Shape s = march3_shape(mode);
-    const int EW = (32 * s.nc / g.P) > 0 ? (32 * s.nc / g.P) : 1;
+    const int nc = march3_nc(g.P, mode);
+    const int EW = (32 * nc / g.P) > 0 ? (32 * nc / g.P) : 1;
     const int strips = g.ney / EW + 1;
     int resident = (int)(smem_sm / (smem_bytes + 1024));
     if (resident > 32) resident = 32;

@@ -41,8 +41,7 @@ int SEM_CAT(march_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& 
     return -2;
 }
 
-// ---- v3 kernel (one warp per strip, TMA-staged, folded tables): even orders, all modes.  Returns 1 when not available.
-#if SEM_P % 2 == 0
+// ---- v3 kernel (one warp per strip, TMA-staged, folded tables): every order, all modes.
 template <int P, int MODE, bool PW>
 static int launch_mode3(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
     constexpr size_t smem = March3Geom<P, MODE>::SMEM_BYTES;
@@ -56,11 +55,9 @@ static int launch_mode3(const MeshDev& g, const MarchArgs& A, const MarchGeom& q
     SEM_CUDA(cudaGetLastError());
     return 0;
 }
-#endif
 
 int SEM_CAT(march3_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q,
                                     cudaStream_t st) {
-#if SEM_P % 2 == 0
     switch (mode) {
         case MODE_K: return launch_mode3<SEM_P, MODE_K, false>(g, A, q, st);
         case MODE_G: return launch_mode3<SEM_P, MODE_G, false>(g, A, q, st);
@@ -72,13 +69,11 @@ int SEM_CAT(march3_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs&
             return (A.d0 || A.e0) ? launch_mode3<SEM_P, MODE_NS, true>(g, A, q, st)
                                   : launch_mode3<SEM_P, MODE_NS, false>(g, A, q, st);
     }
-#endif
     return 1;
 }
 
 // shared memory per CTA (= warp) of the v3 kernel of a mode, 0 when there is none
 size_t SEM_CAT(march3_smem_p, SEM_P)(int mode) {
-#if SEM_P % 2 == 0
     switch (mode) {
         case MODE_K: return March3Geom<SEM_P, MODE_K>::SMEM_BYTES;
         case MODE_G: return March3Geom<SEM_P, MODE_G>::SMEM_BYTES;
@@ -86,15 +81,13 @@ size_t SEM_CAT(march3_smem_p, SEM_P)(int mode) {
         case MODE_CD: return March3Geom<SEM_P, MODE_CD>::SMEM_BYTES;
         case MODE_NS: return March3Geom<SEM_P, MODE_NS>::SMEM_BYTES;
     }
-#endif
     return 0;
 }
 
 // Folded tables of the v3 kernel (layout: Tab3 in sem_march3.cuh).  The folding relies on Ks being centro-symmetric and
 // diag(w) D centro-antisymmetric; the tables handed in are checked for it (they are, for GLL nodes: GLL.py:22-59).
 int SEM_CAT(upload_tab3_p, SEM_P)(const double* D, const double* Ks, const double* w) {
-#if SEM_P % 2 == 0
-    constexpr int P = SEM_P, H = P / 2, n = P + 1, RS = Tab3<P>::RS;
+    constexpr int P = SEM_P, n = P + 1, RS = Tab3<P>::RS, HE = Tab3<P>::HE, HO = Tab3<P>::HO;
     double scaleK = 0.0, scaleD = 0.0, asym = 0.0;
     for (int i = 0; i < n * n; ++i) {
         scaleK = std::fmax(scaleK, std::fabs(Ks[i]));
@@ -110,21 +103,22 @@ int SEM_CAT(upload_tab3_p, SEM_P)(const double* D, const double* Ks, const doubl
         return -2;
     }
     Tab3<P> h;
-    for (int i = 0; i <= H; ++i) {
+    for (int i = 0; i < HE * RS; ++i) h.T[i] = 0.0;
+    for (int i = 0; i < HE; ++i) {
         double* row = h.T + i * RS;
-        for (int k = 0; k <= H; ++k) {
+        for (int k = 0; k < HE; ++k) {
+            const bool mid = (P % 2 == 0) && (k == HE - 1);   // the unpaired middle column of an even order
             const double ka = Ks[i * n + k], kb = Ks[i * n + (P - k)];
             const double da = w[i] * D[i * n + k], db = w[i] * D[i * n + (P - k)];
-            row[2 * k] = (k == H) ? ka : 0.5 * (ka + kb);
-            row[2 * k + 1] = (k == H) ? da : 0.5 * (da + db);
-            if (k < H) {
-                row[2 * (H + 1 + k)] = 0.5 * (ka - kb);
-                row[2 * (H + 1 + k) + 1] = 0.5 * (da - db);
+            row[2 * k] = mid ? ka : 0.5 * (ka + kb);
+            row[2 * k + 1] = mid ? da : 0.5 * (da + db);
+            if (k < HO) {
+                row[2 * (HE + k)] = 0.5 * (ka - kb);
+                row[2 * (HE + k) + 1] = 0.5 * (da - db);
             }
         }
     }
     SEM_CUDA(cudaMemcpyToSymbol(c_tab3<P>, &h, sizeof(h)));
-#endif
     return 0;
 }
 
