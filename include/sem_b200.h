@@ -93,7 +93,9 @@ int sem_ctx_set_tiling(sem_ctx *ctx, int Ty, int Mx);
  * Qx: DEVICE, row-major [NX][NX], column k = k-th generalised eigenvector of the assembled 1-D pencil (K1x, M1x) with the
  * Dirichlet end nodes eliminated (their rows, and the unused trailing columns, are zero), normalised Qx^T M1x Qx = I;
  * lamx[NX]: the eigenvalues (1 for unused columns); Qy, lamy likewise for y.  dirichlet_wesn[4]: which sides carry
- * Dirichlet rows.  The arrays are copied.  Whole mesh on one GPU only. */
+ * Dirichlet rows.  The arrays are copied.  On a partitioned context (after sem_ctx_attach_comm) Qx is the slab's row range
+ * of the GLOBAL matrix, row-major [NX_local][NX_global], lamx[NX_global]; the x transform is then distributed over the ranks
+ * (GEMM + ncclReduceScatter, ncclAllGather + GEMM) and the preconditioner stays the exact inverse. */
 int sem_ctx_set_fdm(sem_ctx *ctx, const double *Qx, const double *lamx, const double *Qy, const double *lamy,
                     const int *dirichlet_wesn);
 

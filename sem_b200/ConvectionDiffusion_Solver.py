@@ -23,7 +23,7 @@ class ConvectionDiffusionSolver:
         Steady convection-diffusion ``Pe [u, v].grad T = lap T`` on [0,L_x]x[0,L_y] with Dirichlet (value) or
         homogeneous Neumann (None) sides -- arguments as CD:10-35.  Extra, optional: ``device`` (CUDA ordinal),
         ``restart`` (Krylov basis size), ``precond`` ('auto' | 'fdm' | 'jacobi' | 'none'; auto = fast diagonalisation of
-        the Laplacian on one GPU, Jacobi on a partitioned mesh), ``partition`` = (rank, world): this process
+        the Laplacian -- of the whole mesh on one GPU, of each rank's slab on a partitioned mesh), ``partition`` = (rank, world): this process
         owns one strip of element columns and takes/returns the matching slab of every global vector.
         """
         self._iprint = iprint
@@ -51,7 +51,7 @@ class ConvectionDiffusionSolver:
         self._buf = [d.zeros() for _ in range(4)]
         self._restart = restart
         if precond == 'auto':
-            precond = 'fdm' if partition is None or int(partition[1]) == 1 else 'jacobi'
+            precond = 'fdm'
         self._precond = {'none': 0, 'jacobi': 1, 'fdm': 2}[precond]
         self._work = None
         self.last_iters = 0

@@ -57,7 +57,7 @@ class NavierStokesSolver:
         self._x = d.zeros(3)
         self._restart = restart
         if precond == 'auto':
-            precond = 'fdm' if partition is None or int(partition[1]) == 1 else 'jacobi'
+            precond = 'fdm'
         self._precond = {'jacobi': 1, 'fdm': 2}[precond]
         self._work = None
         self.last_iters = 0

@@ -504,27 +504,34 @@ int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double
 // fast-diagonalisation preconditioner: spectral scaling and Dirichlet pass-through
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_fdm_scale(const MeshDev g, const double* __restrict__ lx, const double* __restrict__ ly,
-                            double* __restrict__ z) {
+                            double* __restrict__ z, int rows, double floor_) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tot = (long long)g.NX * g.LD;
+    const long long tot = (long long)rows * g.LD;
     if (idx >= tot) return;
     const int ix = (int)(idx / g.LD), iy = (int)(idx % g.LD);
     if (iy >= g.NY) return;
     const double den = lx[ix] + ly[iy];
     // the constant mode of an all-Neumann Laplacian has lx + ly = 0: pseudo-inverse
-    z[idx] = (den > 1e-12 * (lx[g.NX - 1] + ly[g.NY - 1])) ? z[idx] / den : 0.0;
+    z[idx] = (den > floor_) ? z[idx] / den : 0.0;
 }
 
-int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, cudaStream_t st) {
-    const long long tot = (long long)g.NX * g.LD;
-    k_fdm_scale<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, lx, ly, z);
+// z[i][j] /= lx[i] + ly[j] for the `rows` spectral rows of z (lx already offset to the first of them)
+int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, int rows, cudaStream_t st) {
+    const long long tot = (long long)rows * g.LD;
+    if (tot <= 0) return 0;
+    // lx + ly = 0 only for the constant mode of an all-Neumann problem; the largest eigenvalue is ~ P^4 (1/dx^2 + 1/dy^2)
+    // and the eigen-solver's absolute error ~ 1e-16 of that
+    const double p4 = (double)g.P * g.P * g.P * g.P;
+    const double floor_ = 1e-13 * p4 * (1.0 / (g.dx * g.dx) + 1.0 / (g.dy * g.dy));
+    k_fdm_scale<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, lx, ly, z, rows, floor_);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }
 
 struct DirFlags { int d[4]; };
 
-// boundary nodes only: threads 0..NY-1 -> line 0, NY..2NY-1 -> last line, then the first / last column of every line
+// boundary nodes only: threads 0..NY-1 -> line 0, NY..2NY-1 -> last line, then the first / last column of every line.
+// Dirichlet sides (global W / E lines live on the first / last rank only): z = r, the identity rows of the operator.
 __global__ void k_fdm_boundary(const MeshDev g, const DirFlags f, const double* __restrict__ r, double* __restrict__ z) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     int ix, iy;
@@ -533,8 +540,8 @@ __global__ void k_fdm_boundary(const MeshDev g, const DirFlags f, const double* 
     else if (t < 2 * g.NY + g.NX) { ix = t - 2 * g.NY; iy = 0; }
     else if (t < 2 * g.NY + 2 * g.NX) { ix = t - 2 * g.NY - g.NX; iy = g.NY - 1; }
     else return;
-    const bool dir = (ix == 0 && f.d[SIDE_W]) || (ix == g.NX - 1 && f.d[SIDE_E]) || (iy == 0 && f.d[SIDE_S]) ||
-                     (iy == g.NY - 1 && f.d[SIDE_N]);
+    const bool dir = (ix == 0 && !g.has_left && f.d[SIDE_W]) || (ix == g.NX - 1 && !g.has_right && f.d[SIDE_E]) ||
+                     (iy == 0 && f.d[SIDE_S]) || (iy == g.NY - 1 && f.d[SIDE_N]);
     if (dir) z[(long long)ix * g.LD + iy] = r[(long long)ix * g.LD + iy];
 }
 

@@ -74,6 +74,7 @@ struct sem_ctx {
     void* blas_ws;
     double *fQx, *fLx, *fQy, *fLy, *fT1, *fT2;
     int fdm_ready, fdm_dir[4];
+    int fdm_nxg, fdm_block;  // partitioned mesh: global line count and spectral modes per rank (exact distributed FDM)
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
 };
 
@@ -638,48 +639,78 @@ extern "C" int sem_axpby(sem_ctx* c, double a, const double* x, double b, double
 extern "C" int sem_ctx_set_fdm(sem_ctx* c, const double* Qx, const double* lamx, const double* Qy, const double* lamy,
                                const int* dirichlet_wesn) {
     SEM_CHECK_CTX(c);
-    if (c->has_comm || c->g.has_left || c->g.has_right) {
-        set_error("sem_ctx_set_fdm: the global fast-diagonalisation preconditioner needs the whole mesh on one GPU");
+    const size_t nx = (size_t)c->g.NX, ny = (size_t)c->g.NY, ld = (size_t)c->g.LD;
+    const size_t nxg = (size_t)c->g.NXg;                       // == nx on one GPU
+    const int world = c->has_comm ? c->comm.world : 1;
+    if (!c->has_comm && (c->g.has_left || c->g.has_right)) {
+        set_error("sem_ctx_set_fdm: a partitioned context needs its communicator first (sem_ctx_attach_comm)");
         return -2;
     }
-    const size_t nx = (size_t)c->g.NX, ny = (size_t)c->g.NY, vlen = nx * c->g.LD;
-    if (!c->fQx) {
-        SEM_CUDA(cudaMalloc(&c->fQx, sizeof(double) * nx * nx));
-        SEM_CUDA(cudaMalloc(&c->fLx, sizeof(double) * nx));
-        SEM_CUDA(cudaMalloc(&c->fQy, sizeof(double) * ny * ny));
-        SEM_CUDA(cudaMalloc(&c->fLy, sizeof(double) * ny));
-        SEM_CUDA(cudaMalloc(&c->fT1, sizeof(double) * vlen));
-        SEM_CUDA(cudaMalloc(&c->fT2, sizeof(double) * vlen));
-        SEM_CUDA(cudaMemset(c->fT1, 0, sizeof(double) * vlen));   // the GEMMs never touch the pad columns
-        SEM_CUDA(cudaMemset(c->fT2, 0, sizeof(double) * vlen));
+    const size_t block = (nxg + world - 1) / world;            // spectral modes per rank
+    const size_t t_rows = (world > 1) ? block * world : nx;    // rows of the transform buffers
+    if (c->fQx) {
+        cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2);
+        c->fQx = nullptr;
     }
+    SEM_CUDA(cudaMalloc(&c->fQx, sizeof(double) * nx * nxg));
+    SEM_CUDA(cudaMalloc(&c->fLx, sizeof(double) * t_rows));
+    SEM_CUDA(cudaMalloc(&c->fQy, sizeof(double) * ny * ny));
+    SEM_CUDA(cudaMalloc(&c->fLy, sizeof(double) * ny));
+    SEM_CUDA(cudaMalloc(&c->fT1, sizeof(double) * t_rows * ld));
+    SEM_CUDA(cudaMalloc(&c->fT2, sizeof(double) * t_rows * ld));
+    SEM_CUDA(cudaMemset(c->fT1, 0, sizeof(double) * t_rows * ld));   // the GEMMs never touch the pad columns
+    SEM_CUDA(cudaMemset(c->fT2, 0, sizeof(double) * t_rows * ld));
     if (!c->blas) {
         SEM_CUBLAS(cublasCreate(&c->blas));
         SEM_CUDA(cudaMalloc(&c->blas_ws, (size_t)32 << 20));   // fixed workspace: the GEMMs are captured into CUDA graphs
         SEM_CUBLAS(cublasSetWorkspace(c->blas, c->blas_ws, (size_t)32 << 20));
     }
-    SEM_CUDA(cudaMemcpy(c->fQx, Qx, sizeof(double) * nx * nx, cudaMemcpyDeviceToDevice));
-    SEM_CUDA(cudaMemcpy(c->fLx, lamx, sizeof(double) * nx, cudaMemcpyDeviceToDevice));
+    SEM_CUDA(cudaMemcpy(c->fQx, Qx, sizeof(double) * nx * nxg, cudaMemcpyDeviceToDevice));
+    SEM_CUDA(cudaMemset(c->fLx, 0, sizeof(double) * t_rows));
+    SEM_CUDA(cudaMemcpy(c->fLx, lamx, sizeof(double) * nxg, cudaMemcpyDeviceToDevice));
     SEM_CUDA(cudaMemcpy(c->fQy, Qy, sizeof(double) * ny * ny, cudaMemcpyDeviceToDevice));
     SEM_CUDA(cudaMemcpy(c->fLy, lamy, sizeof(double) * ny, cudaMemcpyDeviceToDevice));
     for (int k = 0; k < 4; ++k) c->fdm_dir[k] = dirichlet_wesn[k];
+    c->fdm_nxg = (int)nxg;
+    c->fdm_block = (int)block;
     c->fdm_ready = 1;
     return 0;
 }
 
 // z = K_II^-1 r on the nodes that carry no Dirichlet row, z = r on the Dirichlet nodes.  r and z may not alias.
+// Partitioned mesh: the x transform couples all slabs, so it is distributed -- every rank forms its contribution
+// Qx_r^T R_r to all modes (one GEMM over its own lines; the duplicated interface line is taken from the left rank only), a
+// reduce-scatter over NVLink leaves each rank with a block of modes, the y transforms and the spectral scaling are local to
+// that block, an all-gather returns all modes and one GEMM with the slab's rows of Qx gives the slab of the result.  The
+// preconditioner is the exact inverse on any number of GPUs: the Krylov iteration count does not depend on the partition.
 static int fdm_apply(sem_ctx* c, const double* r, double* z, cudaStream_t st) {
     if (!c->fdm_ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called"); return -2; }
-    const int nx = c->g.NX, ny = c->g.NY, ld = c->g.LD;
+    const int nx = c->g.NX, ny = c->g.NY, ld = c->g.LD, nxg = c->fdm_nxg;
     const double one = 1.0, zero = 0.0;
     SEM_CUBLAS(cublasSetStream(c->blas, st));
     // a row-major [NX][LD] vec is the column-major matrix R^T (ny x nx, leading dimension LD); a row-major Q is the
     // column-major Q^T.  Steps: T1 = Qx^T R, Z = T1 Qy, Z /= (lx + ly), T2 = Z Qy^T, X = Qx T2 -- written for the transposes.
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nx, nx, &one, r, ld, c->fQx, nx, &zero, c->fT1, ld));
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT1, ld, &zero, c->fT2, ld));
-    if (aux_fdm_scale(c->g, c->fLx, c->fLy, c->fT2, st)) return -1;
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT2, ld, &zero, c->fT1, ld));
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nx, &one, c->fT1, ld, c->fQx, nx, &zero, z, ld));
+    if (!c->has_comm) {
+        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nx, nx, &one, r, ld, c->fQx, nx, &zero, c->fT1, ld));
+        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT1, ld, &zero, c->fT2, ld));
+        if (aux_fdm_scale(c->g, c->fLx, c->fLy, c->fT2, nx, st)) return -1;
+        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT2, ld, &zero, c->fT1, ld));
+        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nx, &one, c->fT1, ld, c->fQx, nx, &zero, z, ld));
+        return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
+    }
+    const int B = c->fdm_block, me = c->comm.rank;
+    const int skip = c->g.has_left ? 1 : 0;                    // the interface line is summed from the left rank's copy
+    double* mine1 = c->fT2;                                    // this rank's block of modes (B x LD), then Z
+    double* mine2 = c->fT2 + (size_t)B * ld;                   // T2 block
+    // contribution of this slab to all modes: T1p (nxg x ny) = Qx_r[skip:, :]^T R_r[skip:, :]
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nxg, nx - skip, &one, r + (size_t)skip * ld, ld,
+                           c->fQx + (size_t)skip * nxg, nxg, &zero, c->fT1, ld));
+    if (comm_reduce_scatter_sum(c->comm, c->fT1, mine1, (size_t)B * ld, st)) return -1;
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, B, ny, &one, c->fQy, ny, mine1, ld, &zero, mine2, ld));
+    if (aux_fdm_scale(c->g, c->fLx + (size_t)me * B, c->fLy, mine2, B, st)) return -1;
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, B, ny, &one, c->fQy, ny, mine2, ld, &zero, mine1, ld));
+    if (comm_allgather(c->comm, mine1, c->fT1, (size_t)B * ld, st)) return -1;
+    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nxg, &one, c->fT1, ld, c->fQx, nxg, &zero, z, ld));
     return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
 }
 

@@ -13,6 +13,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -37,6 +39,8 @@ int load_nccl() {
     SEM_SYM(CommInitRank, "ncclCommInitRank")
     SEM_SYM(CommDestroy, "ncclCommDestroy")
     SEM_SYM(AllReduce, "ncclAllReduce")
+    SEM_SYM(ReduceScatter, "ncclReduceScatter")
+    SEM_SYM(AllGather, "ncclAllGather")
     SEM_SYM(Send, "ncclSend")
     SEM_SYM(Recv, "ncclRecv")
     SEM_SYM(GroupStart, "ncclGroupStart")
@@ -90,6 +94,16 @@ void comm_destroy(Comm& c) {
 
 int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st) {
     SEM_NCCL(g_nccl.AllReduce(buf, buf, (size_t)k, ncclDouble, ncclSum, (ncclComm_t)c.nccl, st));
+    return 0;
+}
+
+int comm_reduce_scatter_sum(const Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t st) {
+    SEM_NCCL(g_nccl.ReduceScatter(send, recv, count_per_rank, ncclDouble, ncclSum, (ncclComm_t)c.nccl, st));
+    return 0;
+}
+
+int comm_allgather(const Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t st) {
+    SEM_NCCL(g_nccl.AllGather(send, recv, count_per_rank, ncclDouble, (ncclComm_t)c.nccl, st));
     return 0;
 }
 

@@ -18,6 +18,10 @@ int comm_init(Comm& c, const unsigned char id[128], int rank, int world, int NY)
 void comm_destroy(Comm& c);
 // in-place sum of k doubles over all ranks
 int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st);
+// recv[count_per_rank] = this rank's block of the element-wise sum over ranks of send[world * count_per_rank]
+int comm_reduce_scatter_sum(const Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t st);
+// recv[world * count_per_rank] = concatenation of every rank's send[count_per_rank]
+int comm_allgather(const Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t st);
 // Interface exchange after a local operator apply: every field's interface line(s) hold this rank's element sums;
 // send them to the neighbour(s), receive theirs and add (two-term sum: bitwise identical on both ranks).
 // Two halves so that the caller can run the interior of the operator between them (on another stream):

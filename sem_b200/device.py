@@ -184,11 +184,13 @@ class SemDevice:
         return Q.contiguous(), lam_full
 
     def setup_fdm(self, dirichlet_wesn):
-        """Build and hand over the fast-diagonalisation preconditioner for the given Dirichlet sides (W, E, S, N)."""
-        if self.part is not None and self.part.world > 1:
-            raise L.SemError("the fast-diagonalisation preconditioner needs the whole mesh on one GPU")
+        """Build and hand over the fast-diagonalisation preconditioner for the given Dirichlet sides (W, E, S, N).  On a
+        partitioned mesh the x transform is distributed (GEMM + reduce-scatter, all-gather + GEMM): still the exact inverse."""
         dW, dE, dS, dN = (bool(v) for v in dirichlet_wesn)
-        Qx, lx = self._fdm_1d(self.N_ex, self.dx, dW, dE)
+        Qx, lx = self._fdm_1d(self.N_ex, self.dx, dW, dE)        # the GLOBAL x pencil (every rank solves the same small problem)
+        if self.part is not None and self.part.world > 1:
+            # exact distributed FDM: this rank keeps the rows of Qx that belong to its slab (all modes)
+            Qx = Qx[self.part.line_begin:self.part.line_end + 1].contiguous()
         Qy, ly = self._fdm_1d(self.N_ey, self.dy, dS, dN)
         flags = (C.c_int * 4)(int(dW), int(dE), int(dS), int(dN))
         torch.cuda.current_stream(self.tdev).synchronize()
