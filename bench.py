@@ -177,7 +177,7 @@ def run_ours(args):
     lib = d.lib
 
     def step():
-        # for world > 1 the call ends with the NCCL exchange of the interface node lines
+        # for world > 1 the call ends with the exchange of the interface node lines (peer-memory mailboxes)
         L.check(lib.sem_cd_jvp(d.ctx, C.byref(st), dT.data_ptr(), None, None, out.data_ptr(), d.stream), "sem_cd_jvp")
 
     def sync_all():
@@ -268,6 +268,8 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(), "partition": f"{world} strips of element columns" if world > 1 else "none",
+                   "interface_exchange": {"p2p": "peer-memory mailboxes over NVLink (push kernel + epoch flag), no NCCL "
+                                                 "on the apply path", "nccl": "ncclSend/ncclRecv", "none": "none"}[d.comm_mode],
                    "l2": "inputs larger than L2 (3 x 537 MB read per step)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "sem_march3_kernel<8, MODE_CD, false>", "peak_source": peak_src,

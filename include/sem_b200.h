@@ -101,9 +101,14 @@ int sem_ctx_set_fdm(sem_ctx *ctx, const double *Qx, const double *lamx, const do
 
 /* ---- multi-GPU: one process per GPU, element columns [m_begin, m_end) per rank (sem_mesh_desc).  Rank 0 creates a
  * 128-byte NCCL unique id, the caller distributes it (torch.distributed), every rank attaches.  Afterwards every operator
- * apply ends with the NCCL exchange of the interface node line(s) and every dot product is all-reduced. */
+ * apply ends with the exchange of the interface node line(s) and every dot product is all-reduced (NCCL).  The interface
+ * exchange itself goes through peer memory: each rank owns a mailbox in its HBM that its two neighbours map with
+ * cudaIpcOpenMemHandle at attach time; a push kernel stores the lines into the neighbour's mailbox over NVLink and
+ * releases an epoch flag, the consumer acquires it and adds.  sem_ctx_comm_mode: 0 = no communicator, 1 = NCCL send/recv
+ * fallback (peer mapping unavailable or SEM_B200_NO_P2P set), 2 = peer-memory mailboxes. */
 int sem_nccl_unique_id(unsigned char *out128);
 int sem_ctx_attach_comm(sem_ctx *ctx, const unsigned char *id128, int rank, int world);
+int sem_ctx_comm_mode(const sem_ctx *ctx);
 
 /* ---- host <-> device packing of the reference's dense vectors (the numpy <-> device boundary) ----------------- */
 int sem_h2d(sem_ctx *ctx, const double *host_local, double *vec, void *stream);
@@ -132,7 +137,8 @@ int sem_cd_jvp(sem_ctx *ctx, const sem_cd_state *st, const double *dT, const dou
  * The element columns are processed in segments: the upload of segment s+1, the kernel of segment s and the download of
  * segment s-1 run concurrently (PCIe is full duplex), so the call costs about one direction of the transfer instead of
  * upload + kernel + download.  dT_vec / dres_vec: device vecs that receive the padded input / output (scratch of the
- * caller).  Returns after the result is complete in host_dres.  Not available on a partitioned context. */
+ * caller).  Returns after the result is complete in host_dres.  On a partitioned context the interface line(s) are
+ * exchanged after the last segment and downloaded once more (the download stream is in order). */
 int sem_cd_jvp_host(sem_ctx *ctx, const sem_cd_state *st, const double *host_dT, double *host_dres,
                     double *dT_vec, double *dres_vec, void *stream);
 /* CD._get_update (CD:123-156): solve J dT = rhs; dT holds the initial guess on entry. work >= sem_cd_work_len(). */

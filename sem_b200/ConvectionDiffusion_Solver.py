@@ -144,7 +144,7 @@ class ConvectionDiffusionSolver:
             raise RuntimeError('ConvectionDiffusion: _get_residuals must be called before _get_dresiduals')
         if (du is not None or dv is not None) and not self._have_jac:
             raise RuntimeError('ConvectionDiffusion: _calc_jacobians must be called before passing du/dv')
-        if du is None and dv is None and d.part is None:
+        if du is None and dv is None:
             # host vector in, host vector out: upload, apply and download pipelined over segments of element columns
             a, out = d._host(dT), d.host_result()
             st = self._state(with_jac=False)

@@ -36,7 +36,7 @@ static const struct {
     size_t (*smem3)(int);
 } g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
 
-#define SEM_HOST_SEGMENTS 8   // element-column segments of the host-buffer pipeline
+#define SEM_HOST_SEGMENTS 32  // most element-column segments of the host-buffer pipeline (default 16, SEM_B200_HOST_SEGMENTS)
 #define SEM_GMRES_LAG 6       // Arnoldi steps enqueued ahead of the host-side Givens / convergence test
 
 struct sem_ctx {
@@ -197,6 +197,11 @@ extern "C" int sem_ctx_attach_comm(sem_ctx* c, const unsigned char* id128, int r
     if (comm_init(c->comm, id128, rank, world, c->g.NY)) return -1;
     c->has_comm = 1;
     return 0;
+}
+
+extern "C" int sem_ctx_comm_mode(const sem_ctx* c) {
+    if (!c || !c->has_comm) return 0;
+    return c->comm.p2p ? 2 : 1;
 }
 
 // interface exchange of freshly applied operator outputs (no-op on one GPU)
@@ -522,7 +527,6 @@ extern "C" int sem_cd_jvp(sem_ctx* c, const sem_cd_state* s, const double* dT, c
 extern "C" int sem_cd_jvp_host(sem_ctx* c, const sem_cd_state* s, const double* host_dT, double* host_dres,
                                double* dT_vec, double* dres_vec, void* stream) {
     SEM_CHECK_CTX(c);
-    if (c->has_comm) { set_error("sem_cd_jvp_host: not available on a partitioned context"); return -2; }
     const MeshDev& g = c->g;
     cudaStream_t st = (cudaStream_t)stream;
     if (ensure_stage(c) || ensure_streams(c)) return -1;
@@ -533,7 +537,12 @@ extern "C" int sem_cd_jvp_host(sem_ctx* c, const sem_cd_state* s, const double* 
     // segments of whole 16-column chunks (the chunk size of the kernel), at most SEM_HOST_SEGMENTS
     const int chunk = 16;
     const int nchunks = (g.nex + chunk - 1) / chunk;
-    const int nseg = std::max(1, std::min(SEM_HOST_SEGMENTS, nchunks));
+    static const int want = [] {
+        const char* e = std::getenv("SEM_B200_HOST_SEGMENTS");
+        const int v = e ? std::atoi(e) : 16;
+        return std::max(1, std::min(SEM_HOST_SEGMENTS, v));
+    }();
+    const int nseg = std::max(1, std::min(want, nchunks));
     SEM_CUDA(cudaEventRecord(c->ev_start, st));              // earlier work on the caller's stream (state vectors ...)
     SEM_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_start, 0));
     SEM_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_start, 0));
@@ -554,6 +563,22 @@ extern "C" int sem_cd_jvp_host(sem_ctx* c, const sem_cd_state* s, const double* 
         SEM_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_done[k], 0));
         SEM_CUDA(cudaMemcpyAsync(host_dres + (size_t)dn0 * NY, c->dStageOut + (size_t)dn0 * NY,
                                  sizeof(double) * (dn1 - dn0 + 1) * NY, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    if (c->has_comm && (g.has_left || g.has_right)) {
+        // Partitioned mesh: the interface line(s) downloaded above hold this rank's element sums only.  Exchange them with the
+        // neighbour(s) (peer-memory mailboxes), then download the completed line(s) again -- the download stream is in order,
+        // so the second copy of a line lands after the first.
+        double* f[1] = {dres_vec};
+        if (comm_exchange_add(c->comm, g, f, 1, st)) return -1;
+        const int lines[2] = {g.has_left ? 0 : -1, g.has_right ? g.NX - 1 : -1};
+        for (int q = 0; q < 2; ++q)
+            if (lines[q] >= 0 && aux_unpad_lines(g, dres_vec, c->dStageOut, lines[q], 1, st)) return -1;
+        SEM_CUDA(cudaEventRecord(c->ev_edge, st));
+        SEM_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_edge, 0));
+        for (int q = 0; q < 2; ++q)
+            if (lines[q] >= 0)
+                SEM_CUDA(cudaMemcpyAsync(host_dres + (size_t)lines[q] * NY, c->dStageOut + (size_t)lines[q] * NY,
+                                         sizeof(double) * NY, cudaMemcpyDeviceToHost, c->s_d2h));
     }
     SEM_CUDA(cudaEventRecord(c->ev_end, c->s_d2h));
     SEM_CUDA(cudaStreamWaitEvent(st, c->ev_end, 0));         // the caller's stream stays the single point of ordering

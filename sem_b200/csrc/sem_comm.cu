@@ -1,6 +1,8 @@
 #include "sem_comm.cuh"
 
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -71,6 +73,70 @@ int comm_unique_id(unsigned char out[128]) {
     return 0;
 }
 
+// ---- peer-memory mailboxes --------------------------------------------------------------------------------------------------
+// Layout of a mailbox (see sem_comm.cuh).  Everything a kernel needs to find its slot is computed from these helpers.
+static inline size_t box_data_doubles(const Comm& c) { return (size_t)2 * 2 * c.max_fields * c.slot_len; }
+static inline double* box_slot(const Comm& c, void* box, int parity, int side, int f) {
+    return reinterpret_cast<double*>(box) + ((size_t)(parity * 2 + side) * c.max_fields + f) * c.slot_len;
+}
+enum { BOX_ARRIVED = 0, BOX_SENT = 1, BOX_CONSUMED = 2 };
+static inline unsigned long long* box_word(const Comm& c, void* box, int kind, int side, int f) {
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(box) + box_data_doubles(c));
+    return w + ((size_t)kind * 2 + side) * c.max_fields + f;
+}
+
+// Allocate the mailbox, spread its IPC handle (ncclAllGather of the 64 handle bytes), map the neighbours' mailboxes.
+// All ranks agree on the outcome (all-reduce of a success count): either every rank pushes or every rank uses NCCL.
+static int p2p_init(Comm& c, int NY) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    const bool off = std::getenv("SEM_B200_NO_P2P") != nullptr;
+    ncclComm_t comm = (ncclComm_t)c.nccl;
+    c.slot_len = ((size_t)NY + 15) & ~(size_t)15;
+    const size_t bytes = box_data_doubles(c) * sizeof(double) + (size_t)3 * 2 * c.max_fields * sizeof(unsigned long long);
+    int ok = off ? 0 : 1;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok && cudaMalloc(&c.box, bytes) != cudaSuccess) { cudaGetLastError(); c.box = nullptr; ok = 0; }
+    if (ok) SEM_CUDA(cudaMemset(c.box, 0, bytes));
+    if (ok && cudaIpcGetMemHandle(&mine, c.box) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    // handles of all ranks (64 bytes each) + one double per rank for the agreement
+    unsigned char* dh = nullptr;
+    double* dok = nullptr;
+    SEM_CUDA(cudaMalloc(&dh, (size_t)64 * c.world));
+    SEM_CUDA(cudaMalloc(&dok, sizeof(double)));
+    SEM_CUDA(cudaMemcpy(dh + (size_t)64 * c.rank, &mine, 64, cudaMemcpyHostToDevice));
+    SEM_NCCL(g_nccl.AllGather(dh + (size_t)64 * c.rank, dh, 64, ncclChar, comm, 0));
+    SEM_CUDA(cudaStreamSynchronize(0));
+    std::vector<cudaIpcMemHandle_t> all(c.world);
+    SEM_CUDA(cudaMemcpy(all.data(), dh, (size_t)64 * c.world, cudaMemcpyDeviceToHost));
+    if (ok) {
+        for (int s = 0; s < 2 && ok; ++s) {
+            const int nb = c.rank + (s == 0 ? -1 : 1);
+            if (nb < 0 || nb >= c.world) continue;
+            if (cudaIpcOpenMemHandle(&c.peer_box[s], all[nb], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                c.peer_box[s] = nullptr;
+                ok = 0;
+            }
+        }
+    }
+    const double okd = ok ? 1.0 : 0.0;
+    SEM_CUDA(cudaMemcpy(dok, &okd, sizeof(double), cudaMemcpyHostToDevice));
+    SEM_NCCL(g_nccl.AllReduce(dok, dok, 1, ncclDouble, ncclSum, comm, 0));
+    SEM_CUDA(cudaStreamSynchronize(0));
+    double sum = 0.0;
+    SEM_CUDA(cudaMemcpy(&sum, dok, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dh);
+    cudaFree(dok);
+    c.p2p = (sum > c.world - 0.5) ? 1 : 0;
+    if (!c.p2p) {
+        for (int s = 0; s < 2; ++s)
+            if (c.peer_box[s]) { cudaIpcCloseMemHandle(c.peer_box[s]); c.peer_box[s] = nullptr; }
+        if (std::getenv("SEM_B200_REQUIRE_P2P")) { set_error("peer-memory mailboxes unavailable (SEM_B200_REQUIRE_P2P set)"); return -5; }
+    }
+    return 0;
+}
+
 int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY) {
     if (load_nccl()) return -1;
     ncclUniqueId id;
@@ -82,14 +148,22 @@ int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY
     c.world = world;
     c.max_fields = 4;
     SEM_CUDA(cudaMalloc(&c.recv, sizeof(double) * 2 * c.max_fields * (size_t)NY));
-    return 0;
+    c.p2p = 0;
+    c.box = nullptr;
+    c.peer_box[0] = c.peer_box[1] = nullptr;
+    return p2p_init(c, NY);
 }
 
 void comm_destroy(Comm& c) {
+    for (int s = 0; s < 2; ++s)
+        if (c.peer_box[s]) { cudaIpcCloseMemHandle(c.peer_box[s]); c.peer_box[s] = nullptr; }
     if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
     if (c.recv) cudaFree(c.recv);
+    if (c.box) cudaFree(c.box);
     c.nccl = nullptr;
     c.recv = nullptr;
+    c.box = nullptr;
+    c.p2p = 0;
 }
 
 int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st) {
@@ -125,7 +199,137 @@ __global__ void k_halo_add(const LinePtrs p, int NY) {
     p.line[q][iy] = p.lower_first[q] ? (mine + other) : (other + mine);
 }
 
+// ---- peer-memory exchange ----------------------------------------------------------------------------------------------------
+struct PushArgs {
+    const double* src[8];            // this rank's interface line
+    double* dst[8];                  // parity-0 slot of that line in the neighbour's mailbox
+    unsigned long long* arrived[8];  // the neighbour's epoch flag of the slot (remote)
+    unsigned long long* sent[8];     // local epoch counter of the slot
+    size_t parity_stride;            // doubles between the two parities of a slot
+    int n;
+};
+struct WaitAddArgs {
+    double* line[8];
+    const double* slot[8];           // parity-0 slot in this rank's mailbox
+    unsigned long long* arrived[8];  // local flag, written by the neighbour
+    unsigned long long* consumed[8]; // local epoch counter
+    int lower_first[8];
+    size_t parity_stride;
+    int n;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one CTA per interface line: store it into the neighbour's mailbox (NVLink stores), then release the epoch flag there
+__global__ void __launch_bounds__(1024) k_halo_push(const PushArgs p, int NY) {
+    const int q = blockIdx.x;
+    const unsigned long long e = *p.sent[q] + 1ull;        // every thread reads it before thread 0 advances it (barrier below)
+    double* dst = p.dst[q] + (size_t)(e & 1ull) * p.parity_stride;
+    const double* src = p.src[q];
+    for (int i = threadIdx.x; i < NY; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st_release_sys(p.arrived[q], e);
+        *p.sent[q] = e;
+    }
+}
+
+// one CTA per interface line: wait for the neighbour's epoch, line = own + received (lower rank's term first)
+__global__ void __launch_bounds__(1024) k_halo_wait_add(const WaitAddArgs p, int NY) {
+    const int q = blockIdx.x;
+    __shared__ unsigned long long s_e;
+    if (threadIdx.x == 0) {
+        const unsigned long long e = *p.consumed[q] + 1ull;
+        unsigned long long t0 = 0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(p.arrived[q]) < e) {
+            __nanosleep(64);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 120ull * 1000000000ull) __trap();   // a neighbour died: fail loudly instead of hanging the box
+        }
+        s_e = e;
+    }
+    __syncthreads();
+    const unsigned long long e = s_e;
+    const double* recv = p.slot[q] + (size_t)(e & 1ull) * p.parity_stride;
+    double* line = p.line[q];
+    const bool lf = p.lower_first[q] != 0;
+    for (int i = threadIdx.x; i < NY; i += blockDim.x) {
+        const double mine = line[i], other = __ldcg(recv + i);   // the mailbox is written by a peer: read it from L2
+        line[i] = lf ? (mine + other) : (other + mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *p.consumed[q] = e;
+}
+
+static int p2p_push(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    const size_t last = (size_t)(g.NX - 1) * g.LD;
+    PushArgs a;
+    a.n = 0;
+    a.parity_stride = (size_t)2 * c.max_fields * c.slot_len;
+    for (int f = 0; f < nf; ++f) {
+        if (g.has_left) {   // my left line goes to the left neighbour's "from the right" slot (side 1)
+            a.src[a.n] = fields[f];
+            a.dst[a.n] = box_slot(c, c.peer_box[0], 0, 1, f);
+            a.arrived[a.n] = box_word(c, c.peer_box[0], BOX_ARRIVED, 1, f);
+            a.sent[a.n] = box_word(c, c.box, BOX_SENT, 0, f);
+            a.n++;
+        }
+        if (g.has_right) {  // my right line goes to the right neighbour's "from the left" slot (side 0)
+            a.src[a.n] = fields[f] + last;
+            a.dst[a.n] = box_slot(c, c.peer_box[1], 0, 0, f);
+            a.arrived[a.n] = box_word(c, c.peer_box[1], BOX_ARRIVED, 0, f);
+            a.sent[a.n] = box_word(c, c.box, BOX_SENT, 1, f);
+            a.n++;
+        }
+    }
+    k_halo_push<<<a.n, 1024, 0, st>>>(a, g.NY);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int p2p_wait_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    const size_t last = (size_t)(g.NX - 1) * g.LD;
+    WaitAddArgs a;
+    a.n = 0;
+    a.parity_stride = (size_t)2 * c.max_fields * c.slot_len;
+    for (int f = 0; f < nf; ++f) {
+        if (g.has_left) {
+            a.line[a.n] = fields[f];
+            a.slot[a.n] = box_slot(c, c.box, 0, 0, f);
+            a.arrived[a.n] = box_word(c, c.box, BOX_ARRIVED, 0, f);
+            a.consumed[a.n] = box_word(c, c.box, BOX_CONSUMED, 0, f);
+            a.lower_first[a.n] = 0;   // the neighbour is the lower rank: its partial goes first
+            a.n++;
+        }
+        if (g.has_right) {
+            a.line[a.n] = fields[f] + last;
+            a.slot[a.n] = box_slot(c, c.box, 0, 1, f);
+            a.arrived[a.n] = box_word(c, c.box, BOX_ARRIVED, 1, f);
+            a.consumed[a.n] = box_word(c, c.box, BOX_CONSUMED, 1, f);
+            a.lower_first[a.n] = 1;
+            a.n++;
+        }
+    }
+    k_halo_wait_add<<<a.n, 1024, 0, st>>>(a, g.NY);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    if (c.p2p) {
+        if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
+        if (!g.has_left && !g.has_right) return 0;
+        return p2p_push(c, g, fields, nf, st);
+    }
     static const bool skip = std::getenv("SEM_B200_DEBUG_NO_TRANSFER") != nullptr;   // timing experiments only (wrong results)
     if (skip) return 0;
     if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
@@ -151,6 +355,7 @@ int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* field
 int comm_exchange_finish(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
     if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
     if (!g.has_left && !g.has_right) return 0;
+    if (c.p2p) return p2p_wait_add(c, g, fields, nf, st);
     const size_t NY = (size_t)g.NY;
     const size_t last = (size_t)(g.NX - 1) * g.LD;
     LinePtrs lp;

@@ -1,6 +1,12 @@
 // Multi-GPU plumbing: one process per GPU, NCCL over NVLink.  libnccl is resolved at run time with dlopen (the copy
 // torch already loaded when the process uses torch.distributed; else the system library), so the library has no link
 // dependency on NCCL and single-GPU use needs none.
+//
+// The interface exchange of the partitioned apply does not go through NCCL: every rank owns a mailbox in its own HBM
+// (cudaMalloc + cudaIpc handle, opened by its two neighbours at set-up), a push kernel stores the interface lines straight
+// into the neighbour's mailbox over NVLink and releases a per-line epoch flag there; the consumer kernel acquires the flag
+// and adds.  Epoch counters live in device memory, so the sequence is CUDA-graph replayable.  NCCL send/recv remains as
+// the fallback when peer mapping is unavailable (SEM_B200_NO_P2P=1 forces it for A/B runs).
 #pragma once
 #include "sem_common.cuh"
 
@@ -9,8 +15,15 @@ namespace semb {
 struct Comm {
     void* nccl;        // ncclComm_t
     int rank, world;
-    double* recv;      // device: [2 sides][max_fields][NY] receive staging for the interface lines
+    double* recv;      // device: [2 sides][max_fields][NY] receive staging for the interface lines (NCCL path)
     int max_fields;
+    // peer-memory mailbox (p2p != 0)
+    int p2p;
+    size_t slot_len;                 // doubles per line slot (NY rounded up to 16)
+    void* box;                       // this rank's mailbox: data [2 parities][2 sides][max_fields][slot_len] doubles, then
+                                     // 64-bit words: arrived[2][max_fields] (written by the neighbours),
+                                     // sent[2][max_fields], consumed[2][max_fields] (local epoch counters)
+    void* peer_box[2];               // the left / right neighbour's mailbox mapped into this process (or null)
 };
 
 int comm_unique_id(unsigned char out[128]);

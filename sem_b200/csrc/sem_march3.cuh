@@ -30,6 +30,7 @@
 #include "sem_march.cuh"
 #include "sem_tma.cuh"
 
+#include <cmath>
 #include <type_traits>
 
 namespace semb {
@@ -765,19 +766,21 @@ inline MarchGeom march3_geometry(const MeshDev& g, int mode, int Mx_req, int sm_
     if (resident < 1) resident = 1;
     int Mx = Mx_req;
     if (Mx <= 0) {
-        // A one-warp CTA marches its chunk in sequence (Mx steps + 1 priming step), and the CTAs run in resident rounds:
-        // time ~ ceil(CTAs / slots) * (Mx + 1) steps.  Large meshes: the cost is flat in Mx (16 and 12 columns both
-        // measured 0.37 ms at config 5; longer chunks re-read fewer halo lines, so ties go to the longer chunk).  Small
-        // slabs (8 GPUs on config 5: 120 interior columns) are quantised by the rounds: 6 columns cost 21 steps, 8
-        // columns 27.  Tiny meshes (the reference's own) end up with 2-column chunks: the launch is pure latency.
-        const long long slots = (long long)sm_count * resident;
-        const int ncol = m_hi - m_lo;
-        long long best = -1;
-        for (int cand = 16; cand >= 2; --cand) {
-            const long long ctas = (long long)strips * ((ncol + cand - 1) / cand);
-            const long long cost = ((ctas + slots - 1) / slots) * (cand + 1);
-            if (best < 0 || cost * 100 < best * 98) { best = cost; Mx = cand; }   // a shorter chunk must win by > 2 %
-        }
+        // A one-warp CTA marches its chunk in sequence: Mx steps plus a priming phase worth c ~ 1.5 steps, and the launch
+        // ends with a tail of about kappa * (Mx + c) steps in which the last CTAs finish alone.  With R = strips * ncol /
+        // slots steps of work per resident slot, time ~ R (1 + c / Mx) + kappa (Mx + c) has its minimum at
+        // Mx = sqrt(R c / kappa); c / kappa = 1.4 fits the measured chunk-length sweeps of all three modes on 120 ... 1024
+        // columns (profiles/README.md; e.g. CD: 5 columns on a 128-column slab, 14 on the whole config-5 mesh).  A model
+        // that counts whole resident rounds of CTAs predicted those sweeps badly (CTAs do not run in lock step), and a
+        // balanced decomposition (one CTA per resident slot, each marching an equal share of the flattened (strip,
+        // column) pairs) ran at HALF the speed: concurrently running warps then read line segments scattered over the
+        // whole slab instead of neighbouring segments of the same node lines, and DRAM page locality is lost.
+        // Tiny meshes (the reference's own) end up with 2-column chunks: the launch is pure latency.
+        const double slots = (double)sm_count * resident;
+        const double R = (double)strips * (double)(m_hi - m_lo) / slots;
+        Mx = (int)(sqrt(1.4 * R) + 0.5);
+        if (Mx < 2) Mx = 2;
+        if (Mx > 32) Mx = 32;
     }
     if (Mx > m_hi - m_lo) Mx = m_hi - m_lo;
     q.Ty = EW;

@@ -101,6 +101,11 @@ class SemDevice:
         idbuf = (C.c_ubyte * 128)(*t.cpu().tolist())
         L.check(self.lib.sem_ctx_attach_comm(self.ctx, idbuf, self.part.rank, self.part.world), "sem_ctx_attach_comm")
 
+    @property
+    def comm_mode(self):
+        """'none' | 'nccl' (send/recv fallback) | 'p2p' (peer-memory mailboxes over NVLink) -- how the interface lines travel."""
+        return ("none", "nccl", "p2p")[self.lib.sem_ctx_comm_mode(self.ctx)]
+
     def __del__(self):
         try:
             if getattr(self, "ctx", None):

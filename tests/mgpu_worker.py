@@ -39,6 +39,8 @@ def main():
     T, u, v, dT, du, dv = (rng.standard_normal(cd_o.N) for _ in range(6))
     sl = part.local_slice
     check("cd residual", relerr(cd._get_residuals(sl(T), sl(u), sl(v)), sl(cd_o._get_residuals(T, u, v))), 1e-12)
+    # host vector in / out without du, dv: the pipelined upload / apply / download path with the interface exchange at its end
+    check("cd jvp (host pipeline)", relerr(cd._get_dresiduals(sl(dT)), sl(cd_o._get_dresiduals(dT))), 1e-12)
     cd._calc_jacobians(sl(T))
     cd_o._calc_jacobians(T)
     check("cd jvp", relerr(cd._get_dresiduals(sl(dT), sl(du), sl(dv)), sl(cd_o._get_dresiduals(dT, du, dv))), 1e-12)
@@ -94,8 +96,25 @@ def main():
     check("partitioned fdm solve", relerr(Tp, sl(T1)), 1e-8)
     if not (cdp.last_iters <= cd1.last_iters + 2):
         fails.append(f"rank {rank}: distributed FDM took {cdp.last_iters} iterations (whole mesh: {cd1.last_iters})")
+    xh = np.random.default_rng(5).standard_normal(cd1.N)
+    cd1._get_residuals(xh, uu, vv)
+    cdp._get_residuals(sl(xh), sl(uu), sl(vv))
+    check("partitioned host-pipeline jvp (several segments)", relerr(cdp._get_dresiduals(sl(xh)), sl(cd1._get_dresiduals(xh))), 1e-13)
     if rank == 0:
         print(f"cd solve {cd1.N} nodes: one GPU {cd1.last_iters} its, {world} GPUs {cdp.last_iters} its")
+        print(f"interface exchange: {dpar.comm_mode}")
+
+    # ---- many back-to-back exchanges (graph replays included): the mailbox epochs / parities must never slip.  The K apply
+    #      is linear, so y_k = K^k x (rescaled) on the partition must track the single-GPU sequence.
+    xs, xp = dall.to_device(xg), dpar.to_device(dpar.part.local_slice(xg))
+    ys, yp = dall.zeros(), dpar.zeros()
+    for k in range(40):
+        dall.apply_stiffness(xs, ys)
+        dpar.apply_stiffness(xp, yp)
+        s = 1.0 / float(torch.linalg.vector_norm(ys))
+        xs, ys = ys.mul_(s), xs
+        xp, yp = yp.mul_(s), xp
+    check("40 chained partitioned K applies", relerr(dpar.to_host(xp), dpar.part.local_slice(dall.to_host(xs))), 1e-11)
 
     allf = [None] * world
     dist.all_gather_object(allf, fails)
