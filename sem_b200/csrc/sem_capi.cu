@@ -313,7 +313,12 @@ static int ensure_streams(sem_ctx* c) {
 // lines travel (NCCL send/recv on the caller's stream) while the interior columns are applied on a low-priority side
 // stream, then the received partial sums are added.  `post` is idempotent and cheap, so it simply runs before the
 // transfer (interface lines final) and again after the interior (interior lines final).
-static const int SEM_EDGE_COLUMNS = 4;   // a launch this narrow is pure latency (one warp per strip, 4 marching steps)
+// a launch this narrow is pure latency (one warp per strip, 4 marching steps); SEM_B200_EDGE_COLUMNS=0 disables the split
+// (whole slab in one launch, then the exchange) for A/B runs
+static const int SEM_EDGE_COLUMNS = [] {
+    const char* e = std::getenv("SEM_B200_EDGE_COLUMNS");
+    return e ? std::max(0, std::atoi(e)) : 4;
+}();
 
 typedef std::function<int(cudaStream_t)> postop;
 
@@ -343,10 +348,18 @@ static int partitioned_apply(sem_ctx* c, int mode, MarchArgs& A, double* const* 
         SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));
         SEM_CUDA(cudaStreamWaitEvent(st, c->ev_edge, 0));
     }
-    if (post && post(st)) return -1;
+    if (!post) {
+        // The interface lines are written by the edge launches only: the whole exchange (push, wait for the neighbour, add)
+        // is one kernel that runs while the interior columns are still being applied on the side stream.
+        if (comm_exchange_fused(c->comm, c->g, f, n, st)) return -1;
+        SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
+        return 0;
+    }
+    // with a post-operator (NS: boundary rows recomputed after the interior) the add has to come last
+    if (post(st)) return -1;
     if (comm_exchange_transfer(c->comm, c->g, f, n, st)) return -1;
     SEM_CUDA(cudaStreamWaitEvent(st, c->ev_side, 0));
-    if (post && post(st)) return -1;
+    if (post(st)) return -1;
     return comm_exchange_finish(c->comm, c->g, f, n, st);
 }
 
@@ -363,7 +376,7 @@ static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializ
     const int nex = c->g.nex;
     const int el = c->g.has_left ? std::min(SEM_EDGE_COLUMNS, nex) : 0;
     const int er = c->g.has_right ? std::min(SEM_EDGE_COLUMNS, nex - el) : 0;
-    if (el + er >= nex || n == 0) {   // nothing left to overlap with
+    if (el + er >= nex || el + er == 0 || n == 0) {   // nothing (left) to overlap with
         if (march(c, mode, A, st)) return -1;
         if (post && post(st)) return -1;
         return n ? comm_exchange_add(c->comm, c->g, f, n, st) : 0;

@@ -270,9 +270,76 @@ __global__ void __launch_bounds__(1024) k_halo_wait_add(const WaitAddArgs p, int
     if (threadIdx.x == 0) *p.consumed[q] = e;
 }
 
-static int p2p_push(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+// Both halves in one launch (one CTA per interface line): push the line, then wait for the neighbour's copy of the same
+// line and add it.  Used wherever nothing has to run between the two halves.
+struct ExchangeArgs {
+    PushArgs push;
+    WaitAddArgs add;
+};
+
+__global__ void __launch_bounds__(1024) k_halo_exchange(const ExchangeArgs a, int NY) {
+    const int q = blockIdx.x;
+    __shared__ unsigned long long s_e;
+    {   // ---- push (reads the line before the add below changes it)
+        const PushArgs& p = a.push;
+        const unsigned long long e = *p.sent[q] + 1ull;
+        double* dst = p.dst[q] + (size_t)(e & 1ull) * p.parity_stride;
+        const double* src = p.src[q];
+        for (int i = threadIdx.x; i < NY; i += blockDim.x) dst[i] = src[i];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st_release_sys(p.arrived[q], e);
+            *p.sent[q] = e;
+        }
+    }
+    {   // ---- wait + add
+        const WaitAddArgs& p = a.add;
+        if (threadIdx.x == 0) {
+            const unsigned long long e = *p.consumed[q] + 1ull;
+            unsigned long long t0 = 0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_sys(p.arrived[q]) < e) {
+                __nanosleep(64);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 120ull * 1000000000ull) __trap();
+            }
+            s_e = e;
+        }
+        __syncthreads();
+        const unsigned long long e = s_e;
+        const double* recv = p.slot[q] + (size_t)(e & 1ull) * p.parity_stride;
+        double* line = p.line[q];
+        const bool lf = p.lower_first[q] != 0;
+        for (int i = threadIdx.x; i < NY; i += blockDim.x) {
+            const double mine = line[i], other = __ldcg(recv + i);
+            line[i] = lf ? (mine + other) : (other + mine);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *p.consumed[q] = e;
+    }
+}
+
+static void fill_push(const Comm& c, const MeshDev& g, double* const* fields, int nf, PushArgs& a);
+static void fill_wait_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, WaitAddArgs& a);
+
+int comm_exchange_fused(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
+    if (!g.has_left && !g.has_right) return 0;
+    if (!c.p2p) {
+        if (comm_exchange_transfer(c, g, fields, nf, st)) return -1;
+        return comm_exchange_finish(c, g, fields, nf, st);
+    }
+    ExchangeArgs a;
+    fill_push(c, g, fields, nf, a.push);
+    fill_wait_add(c, g, fields, nf, a.add);   // same (field, side) order as fill_push: line q is sent and completed by CTA q
+    k_halo_exchange<<<a.push.n, 1024, 0, st>>>(a, g.NY);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void fill_push(const Comm& c, const MeshDev& g, double* const* fields, int nf, PushArgs& a) {
     const size_t last = (size_t)(g.NX - 1) * g.LD;
-    PushArgs a;
     a.n = 0;
     a.parity_stride = (size_t)2 * c.max_fields * c.slot_len;
     for (int f = 0; f < nf; ++f) {
@@ -291,14 +358,10 @@ static int p2p_push(const Comm& c, const MeshDev& g, double* const* fields, int 
             a.n++;
         }
     }
-    k_halo_push<<<a.n, 1024, 0, st>>>(a, g.NY);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
 }
 
-static int p2p_wait_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+static void fill_wait_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, WaitAddArgs& a) {
     const size_t last = (size_t)(g.NX - 1) * g.LD;
-    WaitAddArgs a;
     a.n = 0;
     a.parity_stride = (size_t)2 * c.max_fields * c.slot_len;
     for (int f = 0; f < nf; ++f) {
@@ -319,6 +382,19 @@ static int p2p_wait_add(const Comm& c, const MeshDev& g, double* const* fields, 
             a.n++;
         }
     }
+}
+
+static int p2p_push(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    PushArgs a;
+    fill_push(c, g, fields, nf, a);
+    k_halo_push<<<a.n, 1024, 0, st>>>(a, g.NY);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int p2p_wait_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
+    WaitAddArgs a;
+    fill_wait_add(c, g, fields, nf, a);
     k_halo_wait_add<<<a.n, 1024, 0, st>>>(a, g.NY);
     SEM_CUDA(cudaGetLastError());
     return 0;

@@ -42,9 +42,10 @@ int comm_allgather(const Comm& c, const double* send, double* recv, size_t count
 //   comm_exchange_finish:   line = own + received (lower rank's term first).
 int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st);
 int comm_exchange_finish(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st);
+// both halves back to back: ONE kernel on the peer-memory path (push, wait, add per interface line)
+int comm_exchange_fused(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st);
 inline int comm_exchange_add(const Comm& c, const MeshDev& g, double* const* fields, int nf, cudaStream_t st) {
-    if (comm_exchange_transfer(c, g, fields, nf, st)) return -1;
-    return comm_exchange_finish(c, g, fields, nf, st);
+    return comm_exchange_fused(c, g, fields, nf, st);
 }
 
 }  // namespace semb
