@@ -73,8 +73,10 @@ int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double
 
 // ---- fast-diagonalisation preconditioner pieces (see sem_capi.cu) ---------------------------------------------------
 // z[i][iy] /= lx[i] + ly[iy] for `rows` spectral rows (0 for the constant mode of an all-Neumann problem)
-int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, int rows, cudaStream_t st);
+int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, int rows, cudaStream_t st, int batch = 1,
+                  long long batch_stride = 0);
 // z = r on the nodes of the Dirichlet sides (W, E, S, N flags)
-int aux_fdm_boundary(const MeshDev& g, const int* dir_wesn, const double* r, double* z, cudaStream_t st);
+int aux_fdm_boundary(const MeshDev& g, const int* dir_wesn, const double* r, double* z, cudaStream_t st, int batch = 1,
+                     long long batch_stride = 0);
 
 }  // namespace semb

@@ -73,6 +73,7 @@ struct sem_ctx {
     cublasHandle_t blas;
     void* blas_ws;
     double *fQx, *fLx, *fQy, *fLy, *fT1, *fT2;
+    double *fB1, *fB2;        // two-field transform buffers of the batched apply (allocated on first use)
     int fdm_ready, fdm_dir[4];
     int fdm_nxg, fdm_block;  // partitioned mesh: global line count and spectral modes per rank (exact distributed FDM)
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
@@ -165,6 +166,7 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     if (c->has_comm) comm_destroy(c->comm);
     if (c->dStageOut) cudaFree(c->dStageOut);
     if (c->fQx) { cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2); }
+    if (c->fB1) { cudaFree(c->fB1); cudaFree(c->fB2); }
     if (c->blas) { cublasDestroy(c->blas); cudaFree(c->blas_ws); }
     if (c->streams_ready) {
         cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_side2); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_solve); cudaStreamDestroy(c->s_main);
@@ -752,6 +754,34 @@ static int fdm_apply(sem_ctx* c, const double* r, double* z, cudaStream_t st) {
     return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
 }
 
+// Two fields at once (the velocity components of the NS preconditioner, `stride` doubles apart): the same four GEMMs as
+// strided-batched calls, one scaling and one boundary launch -- 6 launches instead of 12.  On the reference's meshes
+// (65 x 65 nodes) every one of them is pure launch latency (4.3 us per GEMM, profiles/README.md).
+static int fdm_apply2(sem_ctx* c, const double* r, double* z, long long stride, cudaStream_t st) {
+    if (c->has_comm) return (fdm_apply(c, r, z, st) || fdm_apply(c, r + stride, z + stride, st)) ? -1 : 0;
+    if (!c->fdm_ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called"); return -2; }
+    const int nx = c->g.NX, ny = c->g.NY, ld = c->g.LD;
+    const long long fs = (long long)nx * ld;
+    if (!c->fB1) {
+        SEM_CUDA(cudaMalloc(&c->fB1, sizeof(double) * 2 * fs));
+        SEM_CUDA(cudaMalloc(&c->fB2, sizeof(double) * 2 * fs));
+        SEM_CUDA(cudaMemset(c->fB1, 0, sizeof(double) * 2 * fs));   // the GEMMs never touch the pad columns
+        SEM_CUDA(cudaMemset(c->fB2, 0, sizeof(double) * 2 * fs));
+    }
+    const double one = 1.0, zero = 0.0;
+    SEM_CUBLAS(cublasSetStream(c->blas, st));
+    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nx, nx, &one, r, ld, stride, c->fQx, nx, 0, &zero,
+                                         c->fB1, ld, fs, 2));
+    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, 0, c->fB1, ld, fs, &zero,
+                                         c->fB2, ld, fs, 2));
+    if (aux_fdm_scale(c->g, c->fLx, c->fLy, c->fB2, nx, st, 2, fs)) return -1;
+    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, 0, c->fB2, ld, fs, &zero,
+                                         c->fB1, ld, fs, 2));
+    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nx, &one, c->fB1, ld, fs, c->fQx, nx, 0, &zero,
+                                         z, ld, stride, 2));
+    return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st, 2, stride);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Right-preconditioned restarted GMRES with CGS2 orthogonalisation (two classical Gram-Schmidt passes, each one
 // batched dot kernel + one batched update kernel).  Replaces scipy.sparse.linalg.lgmres of CD:146-148 / NS:222-224.
@@ -998,7 +1028,7 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
     vecop Pinv = [&](const double* r, double* z) {
         if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, n, st);
         if (kr->precond == 2) {
-            if (fdm_apply(c, r, z, st) || fdm_apply(c, r + vlen, z + vlen, st)) return -1;
+            if (fdm_apply2(c, r, z, vlen, st)) return -1;
         } else if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) {
             return -1;
         }
