@@ -117,7 +117,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(args.steps, 20)
+    steps = max(args.steps, 1)             # exactly K timed steps, like the GPU arm
     val, dt, n = cpu_apply_sample(steps, max(args.warmup, 3))
     cores = len(os.sched_getaffinity(0))
     sample = f"{CPU_SAMPLE_NE}x{CPU_SAMPLE_NE} elements, P={P_ORDER} ({n} nodes), scipy CSR mat-vec, {steps} applies"
