@@ -160,3 +160,70 @@ def test_boussinesq_coupler_logic_on_the_oracle_solvers():
     assert out["JNK"][4]["nonlinear_its"] < out["GS"][4]["nonlinear_its"]
     assert mod.study_title('JNK', 1e3, 1e3, 0.71, 4, 8, 1e-10, 8, 0.8, 0.2, 1e-13, 20, 1e-13) == \
         "BoussinesqJNK_1.0e+03~1.0e+03~0.71_4~8_1e-10_1e-13~20_1e-13"
+
+
+def _gmres_right(A, b, Pinv, tol, maxit):
+    """Plain right-preconditioned GMRES (CGS2), numpy: x = sum_k y_k Pinv(v_k)."""
+    n = b.size
+    beta = np.linalg.norm(b)
+    V = np.zeros((maxit + 1, n)); Z = np.zeros((maxit, n)); H = np.zeros((maxit + 1, maxit))
+    V[0] = b / beta
+    for k in range(maxit):
+        Z[k] = Pinv(V[k]); w = A(Z[k])
+        for _ in range(2):
+            h = V[:k + 1] @ w; w -= h @ V[:k + 1]; H[:k + 1, k] += h
+        H[k + 1, k] = np.linalg.norm(w); V[k + 1] = w / H[k + 1, k]
+        e1 = np.zeros(k + 2); e1[0] = beta
+        y, res = np.linalg.lstsq(H[:k + 2, :k + 1], e1, rcond=None)[:2]
+        if np.linalg.norm(H[:k + 2, :k + 1] @ y - e1) <= tol:
+            break
+    return y @ Z[:k + 1], k + 1
+
+
+def test_null_vector_structure_and_member_selection():
+    """Facts about the singular NS Jacobian that the device solver's preconditioner relies on:
+    (1) the pressure part of the left null vector is the tensor product (1 - L_P(xi)) x (1 - L_P(eta)), element by element,
+    independent of the linearisation point; (2) right-preconditioned GMRES with the block lower-triangular preconditioner
+    lands on the reference's member of the solution set for ANY Schur-block preconditioner once that is given the rank-one
+    correction z <- z - l_c (m_c.z - l_c.r) / (m_c.l_c), m_c = M_p l_c -- and on a different member without it."""
+    import scipy.sparse.linalg as spla
+    from numpy.polynomial import legendre as npl
+    P, ne = 4, 4
+    ns = so.NSOracle(1.0, 1.0, 50.0, 0.0, P, ne, ne, u_N=1.0, mtol=1e-13, mtol_newton=1e-13)
+    N, n1 = ns.N, ne * P + 1
+    T = np.zeros(N)
+    u, v, p = ns._get_solution(T, max_newton=2)
+    ru, rv, rc = ns._get_residuals(u, v, p, T)
+    ns._calc_jacobians(u, v)
+    J = ns.jacobian_matrix().tocsr()
+    l = ns._left_null(J.tocsc())
+    assert l is not None
+    lc = l[2 * N:]
+    one_minus_LP = np.tile((1.0 - npl.legval(so.gll(P)[0], [0] * P + [1]))[:-1], ne)
+    one_minus_LP = np.append(one_minus_LP, 0.0)
+    model = np.outer(one_minus_LP, one_minus_LP).ravel()
+    c = (model @ lc) / (model @ model)
+    assert np.linalg.norm(lc - c * model) < 1e-10 * np.linalg.norm(lc)
+    b = -np.hstack((ru, rv, rc))
+    x_ref = np.hstack(ns._get_update(-ru, -rv, -rc))
+    Mp = ns._M.copy(); Mp[ns._pin] = 1.0
+    mc = Mp * lc
+    lu = spla.splu(J[:2 * N, :2 * N].tocsc()); C = J[2 * N:, :2 * N].tocsr()
+    Dr = np.exp(np.random.default_rng(1).uniform(-1, 1, N))
+    other = lambda y: Dr * y / Mp
+    def corrected(y):
+        z = other(y)
+        return z - lc * ((mc @ z - lc @ y) / (mc @ lc))
+    def tri(Sinv):
+        def f(r):
+            za = lu.solve(r[:2 * N])
+            return np.hstack((za, Sinv(r[2 * N:] - C @ za)))
+        return f
+    tol = 1e-11 * np.linalg.norm(b)      # stop AT convergence: on a singular system further steps drift along the null vector
+    errs = {}
+    for name, Si in (("mass", lambda y: y / Mp), ("other", other), ("corrected", corrected)):
+        x, its = _gmres_right(lambda z: J @ z, b, tri(Si), tol, 400)
+        assert its < 400 and np.linalg.norm(J @ x - b) < 1e-9 * np.linalg.norm(b), name
+        errs[name] = relerr(x[2 * N:], x_ref[2 * N:])
+    assert errs["mass"] < 1e-8 and errs["corrected"] < 1e-8
+    assert errs["other"] > 1e-4
