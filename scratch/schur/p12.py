@@ -102,3 +102,37 @@ for name, Si in cands:
     x, its, hist = gmres_right(lambda z: J @ z, b, tri(Si), tol, 700 if N > 10000 else 1500)
     print(f'{name:28s} its {its:5d} |Jx-b|/|b| {np.linalg.norm(J @ x - b) / np.linalg.norm(b):.1e}  p diff vs reference member '
           f'{np.linalg.norm(x[2*N:] - x_ref[2*N:]) / np.linalg.norm(x_ref[2*N:]):.1e}  vel diff {np.linalg.norm(x[:2*N] - x_ref[:2*N]) / max(np.linalg.norm(x_ref[:2*N]), 1e-300):.1e}  t {time.time() - t:.1f}', flush=True)
+# ---- with a pressure-convection-diffusion fine stage instead of the mass sweep (interior), Re > 0
+if newton > 0:
+    K = ns._K.tocsr()
+    Fp = (K + Re * (sps.diags(ns._u) @ ns._G_x + sps.diags(ns._v) @ ns._G_y)).tocsr()
+    KIB_BBinv_DBI = None
+    # reduced operators on the interior (boundary values slaved by the Neumann rows): X_red = X_II - X_IB K_BB^-1 K_BI
+    def red(X):
+        XII = X[Ii][:, Ii].toarray(); XIB = X[Ii][:, Bi].toarray()
+        return XII - XIB @ luBB.solve(DBI.toarray())
+    Kred = red(K); Fred = red(Fp)
+    Kri = np.linalg.pinv(Kred, rcond=1e-11)
+    def schur_two_level_pcd(y):
+        z1 = np.zeros(N); z1[Ii] = coarse_interior(y[Ii])
+        z1[Bi] = luBB.solve(y[Bi] - DBI @ z1[Ii])
+        r1 = y - S0(z1)
+        z2 = np.zeros(N); z2[Ii] = (Fred @ (Kri @ r1[Ii])) / Mp[Ii]
+        z2[Bi] = luBB.solve(r1[Bi] - DBI @ z2[Ii])
+        return z1 + z2
+    def pcd_bb(y):
+        z = np.zeros(N); z[Ii] = (Fred @ (Kri @ y[Ii])) / Mp[Ii]; z[Bi] = luBB.solve(y[Bi] - DBI @ z[Ii]); return z
+    luA = spla.splu(J[:2 * N, :2 * N].tocsc())
+    def tri_exact(Sinv):
+        def f(r):
+            za = luA.solve(r[:2 * N]); zp = Sinv(r[2 * N:] - C @ za)
+            return np.hstack((za, zp))
+        return f
+    for name, pre in (('PCD + K_BB (Stokes velocity block)', tri(corrected(pcd_bb))),
+                      ('two-level + PCD (Stokes velocity block)', tri(corrected(schur_two_level_pcd))),
+                      ('mass, EXACT velocity block', tri_exact(mass)),
+                      ('two-level + PCD, EXACT velocity block', tri_exact(corrected(schur_two_level_pcd)))):
+        t = time.time()
+        x, its, hist = gmres_right(lambda z: J @ z, b, pre, tol, 1500)
+        print(f'{name:42s} its {its:5d} |Jx-b|/|b| {np.linalg.norm(J @ x - b) / np.linalg.norm(b):.1e}  p diff '
+              f'{np.linalg.norm(x[2*N:] - x_ref[2*N:]) / np.linalg.norm(x_ref[2*N:]):.1e}  t {time.time() - t:.1f}', flush=True)
