@@ -69,7 +69,8 @@ typedef struct {
     int restart;           /* Krylov basis size per cycle */
     int max_iters;         /* total iteration cap */
     int precond;           /* 0 none, 1 Jacobi, 2 fast diagonalisation (needs sem_ctx_set_fdm); NS: block lower-
-                              triangular with that velocity block, see DESIGN.md */
+                              triangular with that velocity block; NS only, EXPERIMENTAL: 3 = 2 + block
+                              elimination of the boundary pressure rows (needs sem_ctx_set_pbb) */
     int verbose;
     /* outputs */
     int iters;             /* operator applications spent */
@@ -98,6 +99,13 @@ int sem_ctx_set_tiling(sem_ctx *ctx, int Ty, int Mx);
  * (GEMM + ncclReduceScatter, ncclAllGather + GEMM) and the preconditioner stays the exact inverse. */
 int sem_ctx_set_fdm(sem_ctx *ctx, const double *Qx, const double *lamx, const double *Qy, const double *lamy,
                     const int *dirichlet_wesn);
+
+/* EXPERIMENTAL (written at the end of round 1, compiled but not yet validated on a GPU; nothing uses it unless
+ * sem_krylov.precond == 3): boundary block of the NS pressure rows.  idx_host[nb]: offsets ix*LD + iy of the boundary pressure
+ * nodes (the pin node left out); inv_dev: DEVICE, row-major nb x nb inverse of the stiffness matrix restricted to those nodes
+ * (rows K[mask,:] of NS:119,157).  The NS preconditioner then solves the boundary rows exactly, z_B = K_BB^-1 (r_B - K_BI z_I),
+ * instead of scaling them by 1/M.  One GPU only.  The arrays are copied. */
+int sem_ctx_set_pbb(sem_ctx *ctx, const long long *idx_host, int nb, const double *inv_dev);
 
 /* ---- multi-GPU: one process per GPU, element columns [m_begin, m_end) per rank (sem_mesh_desc).  Rank 0 creates a
  * 128-byte NCCL unique id, the caller distributes it (torch.distributed), every rank attaches.  Afterwards every operator

@@ -26,7 +26,8 @@ class NavierStokesSolver:
                  mtol=1e-7, mtol_newton=1e-5, iprint: list = ['NEWTON_suc', 'NEWTON_iter'],
                  device: int = None, restart: int = None, max_newton: int = 50, partition=None, precond: str = 'auto'):
         """Arguments as NS:11-41.  Extra, optional: ``device``, ``restart`` (Krylov basis size), ``max_newton``,
-        ``precond`` of the velocity block ('auto' | 'fdm' | 'jacobi'; auto = fast diagonalisation on one GPU)."""
+        ``precond`` of the velocity block ('auto' | 'fdm' | 'jacobi'; auto = fast diagonalisation on one GPU;
+        'fdm+bb' = experimental, see ``_krylov``)."""
         self._iprint = iprint
         self._Re = Re
         self._Gr = Gr
@@ -58,7 +59,7 @@ class NavierStokesSolver:
         self._restart = restart
         if precond == 'auto':
             precond = 'fdm'
-        self._precond = {'jacobi': 1, 'fdm': 2}[precond]
+        self._precond = {'jacobi': 1, 'fdm': 2, 'fdm+bb': 3}[precond]   # 'fdm+bb': experimental, see _krylov
         self._work = None
         self.last_iters = 0
         self.last_resnorm = float('nan')
@@ -120,8 +121,13 @@ class NavierStokesSolver:
         kr.atol = float(self._mtol * np.sqrt(self.N))            # NS:223
         kr.restart = self._restart
         kr.max_iters = max(2000, 10 * self._restart)
-        if self._precond == 2 and not self._dev.has_fdm:
+        if self._precond in (2, 3) and not self._dev.has_fdm:
             self._dev.setup_fdm([1, 1, 1, 1])                    # velocity Dirichlet rows on all four sides (NS:78-88)
+        if self._precond == 3 and not self._dev.has_pbb:
+            # EXPERIMENTAL, opt-in (precond='fdm+bb'), not validated on a GPU in round 1: block elimination of the
+            # pressure-Neumann boundary rows in the preconditioner (3.5x fewer iterations in the CPU
+            # study, same member of the solution set)
+            self._dev.setup_pressure_boundary_block(int(self.N / 2))
         kr.precond = self._precond
         kr.verbose = 2 if 'LGMRES_iter' in self._iprint else 0
         return kr

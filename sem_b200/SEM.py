@@ -179,3 +179,35 @@ def eval_interpolation(u_e: np.ndarray, points_e: np.ndarray, points_plot: typin
     Sy = GLL.standard_evaluation_matrix(P, eta_p)     # [b, l]
     tmp = np.einsum('ankl,ak->anl', u_e[m_p], Sx)     # contract x inside each plot column's element column
     return np.einsum('abl,bl->ab', tmp[:, n_p, :], Sy)
+
+
+# ---- boundary block of the pressure rows (experimental NS preconditioner stage) ---------------------
+def assembled_1d(A_s: np.ndarray, N_e: int) -> np.ndarray:
+    """Dense 1-D assembly of N_e copies of a (P+1) x (P+1) element matrix with one shared node (the x or y factor of the
+    Kronecker-structured global matrices of SEM.py:170-223)."""
+    n = A_s.shape[0]
+    P = n - 1
+    A = np.zeros((N_e * P + 1, N_e * P + 1))
+    for m in range(N_e):
+        A[m * P:m * P + n, m * P:m * P + n] += A_s
+    return A
+
+
+def pressure_boundary_block(P: int, N_ex: int, N_ey: int, dx: float, dy: float, pin: int = None):
+    """Nodes and matrix of the pressure-Neumann rows restricted to the boundary: returns ``(ix, iy, K_BB)`` with the boundary
+    nodes of the mesh (W line, E line, then the S / N nodes of the lines in between; the node with global index ``pin`` is
+    left out) and ``K_BB[a, b] = K[node_a, node_b]`` for ``K = K1x (x) M1y + M1x (x) K1y`` (SEM.py:186-203, the rows the
+    reference puts into the continuity block at boundary nodes, NS:119,157)."""
+    NX, NY = N_ex * P + 1, N_ey * P + 1
+    Ks, w = GLL.standard_stiffness_matrix(P), GLL.standard_nodes(P)[1]
+    K1x, K1y = assembled_1d(2.0 / dx * Ks, N_ex), assembled_1d(2.0 / dy * Ks, N_ey)
+    M1x, M1y = np.diag(assembled_1d(dx / 2.0 * np.diag(w), N_ex)), np.diag(assembled_1d(dy / 2.0 * np.diag(w), N_ey))
+    ix = np.concatenate([np.zeros(NY, int), np.full(NY, NX - 1), np.repeat(np.arange(1, NX - 1), 2)])
+    iy = np.concatenate([np.arange(NY), np.arange(NY), np.tile([0, NY - 1], NX - 2)])
+    if pin is not None:
+        keep = (iy + NY * ix) != pin
+        ix, iy = ix[keep], iy[keep]
+    same_x = ix[:, None] == ix[None, :]
+    same_y = iy[:, None] == iy[None, :]
+    KBB = K1x[ix[:, None], ix[None, :]] * (M1y[iy][:, None] * same_y) + (M1x[ix][:, None] * same_x) * K1y[iy[:, None], iy[None, :]]
+    return ix, iy, KBB

@@ -501,6 +501,40 @@ int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Boundary block of the NS pressure rows (experimental, sem_ctx_set_pbb): gather / scatter of the boundary pressure nodes
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_pbb_zero(double* __restrict__ z, const long long* __restrict__ idx, int nb) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < nb) z[idx[a]] = 0.0;
+}
+__global__ void k_pbb_gather(const double* __restrict__ r, const double* __restrict__ q, const long long* __restrict__ idx,
+                             int nb, double* __restrict__ rhs) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < nb) rhs[a] = r[idx[a]] - q[idx[a]];
+}
+__global__ void k_pbb_scatter(const double* __restrict__ zb, const long long* __restrict__ idx, int nb,
+                              double* __restrict__ z) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < nb) z[idx[a]] = zb[a];
+}
+
+int aux_pbb_zero(double* z, const long long* idx, int nb, cudaStream_t st) {
+    k_pbb_zero<<<(nb + 255) / 256, 256, 0, st>>>(z, idx, nb);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+int aux_pbb_gather(const double* r, const double* q, const long long* idx, int nb, double* rhs, cudaStream_t st) {
+    k_pbb_gather<<<(nb + 255) / 256, 256, 0, st>>>(r, q, idx, nb, rhs);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+int aux_pbb_scatter(const double* zb, const long long* idx, int nb, double* z, cudaStream_t st) {
+    k_pbb_scatter<<<(nb + 255) / 256, 256, 0, st>>>(zb, idx, nb, z);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // fast-diagonalisation preconditioner: spectral scaling and Dirichlet pass-through
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_fdm_scale(const MeshDev g, const double* __restrict__ lx, const double* __restrict__ ly,

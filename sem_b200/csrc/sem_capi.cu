@@ -74,6 +74,11 @@ struct sem_ctx {
     void* blas_ws;
     double *fQx, *fLx, *fQy, *fLy, *fT1, *fT2;
     double *fB1, *fB2;        // two-field transform buffers of the batched apply (allocated on first use)
+    // boundary block of the NS pressure rows (sem_ctx_set_pbb, experimental): offsets of the boundary pressure nodes, the
+    // dense inverse of K restricted to them (row-major nb x nb), gathered right-hand side and solution
+    long long* pbb_idx;
+    double *pbb_inv, *pbb_rhs, *pbb_z;
+    int pbb_n;
     int fdm_ready, fdm_dir[4];
     int fdm_nxg, fdm_block;  // partitioned mesh: global line count and spectral modes per rank (exact distributed FDM)
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
@@ -167,6 +172,7 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
     if (c->dStageOut) cudaFree(c->dStageOut);
     if (c->fQx) { cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2); }
     if (c->fB1) { cudaFree(c->fB1); cudaFree(c->fB2); }
+    if (c->pbb_idx) { cudaFree(c->pbb_idx); cudaFree(c->pbb_inv); cudaFree(c->pbb_rhs); cudaFree(c->pbb_z); }
     if (c->blas) { cublasDestroy(c->blas); cudaFree(c->blas_ws); }
     if (c->streams_ready) {
         cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_side2); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_solve); cudaStreamDestroy(c->s_main);
@@ -754,6 +760,49 @@ static int fdm_apply(sem_ctx* c, const double* r, double* z, cudaStream_t st) {
     return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (not validated on a GPU in round 1, off unless sem_krylov.precond == 3): boundary block of the NS pressure
+// rows.  The pressure-Neumann rows K[mask,:] p (NS:119,157) are scaled by 1/M in the reference's Schur preconditioner, which
+// leaves eigenvalues ~ 2e4 and costs two thirds of the Krylov iterations (scratch/schur/p12.py).  Block
+// elimination instead:  z_I = mass sweep as before,  z_B = K_BB^-1 (r_B - K_BI z_I)  with the dense inverse of K restricted
+// to the boundary pressure nodes (a ring of 4(n-1) nodes; the pin node is excluded and keeps its identity row).  The member
+// of the singular system's solution set is unchanged: l_c vanishes on the boundary, so S~^T l_c = M_p l_c still holds.
+// idx_host[nb]: offsets ix*LD + iy of the boundary nodes;  inv_dev: DEVICE, row-major nb x nb.  One GPU only.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int sem_ctx_set_pbb(sem_ctx* c, const long long* idx_host, int nb, const double* inv_dev) {
+    SEM_CHECK_CTX(c);
+    if (c->has_comm) { set_error("sem_ctx_set_pbb: not available on a partitioned context"); return -2; }
+    if (nb <= 0 || !idx_host || !inv_dev) { set_error("sem_ctx_set_pbb: bad arguments"); return -2; }
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    for (int a = 0; a < nb; ++a)
+        if (idx_host[a] < 0 || idx_host[a] >= vlen) { set_error("sem_ctx_set_pbb: node offset out of range"); return -2; }
+    if (c->pbb_idx) { cudaFree(c->pbb_idx); cudaFree(c->pbb_inv); cudaFree(c->pbb_rhs); cudaFree(c->pbb_z); c->pbb_idx = nullptr; }
+    c->pbb_n = 0;
+    SEM_CUDA(cudaMalloc(&c->pbb_idx, sizeof(long long) * nb));
+    SEM_CUDA(cudaMalloc(&c->pbb_inv, sizeof(double) * (size_t)nb * nb));
+    SEM_CUDA(cudaMalloc(&c->pbb_rhs, sizeof(double) * nb));
+    SEM_CUDA(cudaMalloc(&c->pbb_z, sizeof(double) * nb));
+    SEM_CUDA(cudaMemcpy(c->pbb_idx, idx_host, sizeof(long long) * nb, cudaMemcpyHostToDevice));
+    SEM_CUDA(cudaMemcpy(c->pbb_inv, inv_dev, sizeof(double) * (size_t)nb * nb, cudaMemcpyDeviceToDevice));
+    c->pbb_n = nb;
+    return 0;
+}
+
+// z_p (already holding the mass sweep) -> boundary entries replaced by K_BB^-1 (r_B - K_BI z_I); q: scratch vec
+static int pbb_apply(sem_ctx* c, const double* rc, double* zp, double* q, cudaStream_t st) {
+    const int nb = c->pbb_n;
+    if (nb <= 0) { set_error("pbb_apply: sem_ctx_set_pbb has not been called"); return -2; }
+    if (aux_pbb_zero(zp, c->pbb_idx, nb, st)) return -1;
+    // (K z)[boundary nodes] with z_B = 0 is K_BI z_I (the pin node, if it lies on the boundary, is skipped and keeps r_pin)
+    if (aux_neumann_rows(c->g, c->tab(), zp, q, c->pin_gx, c->pin_iy, 1, st)) return -1;
+    if (aux_pbb_gather(rc, q, c->pbb_idx, nb, c->pbb_rhs, st)) return -1;
+    const double one = 1.0, zero = 0.0;
+    SEM_CUBLAS(cublasSetStream(c->blas, st));
+    // row-major INV is the column-major INV^T: y = (INV^T)^T x
+    SEM_CUBLAS(cublasDgemv(c->blas, CUBLAS_OP_T, nb, nb, &one, c->pbb_inv, nb, c->pbb_rhs, 1, &zero, c->pbb_z, 1));
+    return aux_pbb_scatter(c->pbb_z, c->pbb_idx, nb, zp, st);
+}
+
 // Two fields at once (the velocity components of the NS preconditioner, `stride` doubles apart): the same four GEMMs as
 // strided-batched calls, one scaling and one boundary launch -- 6 launches instead of 12.  On the reference's meshes
 // (65 x 65 nodes) every one of them is pure launch latency (4.3 us per GEMM, profiles/README.md).
@@ -1027,7 +1076,7 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
     // solution family as the reference's Schur-complement iteration -- see DESIGN.md.
     vecop Pinv = [&](const double* r, double* z) {
         if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, n, st);
-        if (kr->precond == 2) {
+        if (kr->precond == 2 || kr->precond == 3) {
             if (fdm_apply2(c, r, z, vlen, st)) return -1;
         } else if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) {
             return -1;
@@ -1035,7 +1084,9 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
         MarchArgs A = zero_args();
         A.a = z; A.b = z + vlen; A.y0 = tmp;
         if (apply_and_exchange(c, MODE_DIV, A, {tmp}, st)) return -1;
-        return aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st);
+        if (aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st)) return -1;
+        if (kr->precond == 3) return pbb_apply(c, r + 2 * vlen, z + 2 * vlen, tmp, st);   // experimental, see sem_ctx_set_pbb
+        return 0;
     };
     GmresLayout L{n, 3, vlen};
     const int rc = gmres(c, L, Aop, Pinv, rhs3, x3, kr, V, w, t, vin, st, use_graph);

@@ -83,6 +83,7 @@ class SemDevice:
         self.N_local = self.NX * self.NY
         self._pinned = {}
         self.has_fdm = False
+        self.has_pbb = False
         if self.part is not None and self.part.world > 1:
             self._attach_comm()
 
@@ -202,6 +203,23 @@ class SemDevice:
         L.check(self.lib.sem_ctx_set_fdm(self.ctx, Qx.data_ptr(), lx.data_ptr(), Qy.data_ptr(), ly.data_ptr(), flags),
                 "sem_ctx_set_fdm")
         self.has_fdm = True
+
+    def setup_pressure_boundary_block(self, pin):
+        """EXPERIMENTAL (not validated on a GPU in round 1; used only by ``NavierStokesSolver(precond='fdm+bb')``): dense
+        inverse of the stiffness matrix restricted to the boundary pressure nodes, for the block elimination of the
+        pressure-Neumann rows in the NS preconditioner.  Whole mesh on one GPU, at most 8192 boundary
+        nodes (a banded ring solve is the production answer)."""
+        from . import SEM
+        if self.part is not None and self.part.world > 1:
+            raise L.SemError("the pressure boundary block needs the whole mesh on one GPU")
+        ix, iy, KBB = SEM.pressure_boundary_block(self.P, self.N_ex, self.N_ey, self.dx, self.dy, pin)
+        if ix.size > 8192:
+            raise L.SemError(f"pressure boundary block: {ix.size} boundary nodes exceed the dense limit of 8192")
+        inv = torch.linalg.inv(torch.from_numpy(KBB).to(self.tdev)).contiguous()
+        idx = np.ascontiguousarray(ix.astype(np.int64) * self.LD + iy.astype(np.int64))
+        torch.cuda.current_stream(self.tdev).synchronize()
+        L.check(self.lib.sem_ctx_set_pbb(self.ctx, idx.ctypes.data, int(idx.size), inv.data_ptr()), "sem_ctx_set_pbb")
+        self.has_pbb = True
 
     # ---- single operators ------------------------------------------------------------------------------------------
     def apply_stiffness(self, x, y):

@@ -97,3 +97,22 @@ def test_pinned_result_pool_recycles_only_dead_arrays(monkeypatch):
     assert len(D._PINNED_POOL[12]) == 1
     c = D._pinned_result(12)                         # recycled block
     assert D._PINNED_POOL[12] == [] and c.shape == (12,)
+
+
+@pytest.mark.parametrize("P,nx,ny,Lx,Ly", [(4, 5, 3, 1.3, 0.7), (3, 4, 4, 1.0, 1.0), (8, 2, 3, 2.0, 1.0), (1, 3, 2, 1.0, 1.0)])
+def test_pressure_boundary_block_matches_oracle(P, nx, ny, Lx, Ly):
+    """Host set-up of the (experimental) boundary-block stage of the NS preconditioner: node list and K_BB against the
+    boundary rows / columns of the oracle's assembled Jacobian (rows K[mask,:] of NS:119,157)."""
+    from oracle import sem_oracle as so   # checker
+    from sem_b200 import SEM
+    ns = so.NSOracle(Lx, Ly, 10.0, 0.0, P, nx, ny, u_N=1.0)
+    z = np.zeros(ns.N)
+    ns._get_residuals(z, z, z, z)
+    ns._calc_jacobians(z, z)
+    D = ns.jacobian_matrix().tocsr()[2 * ns.N:, 2 * ns.N:]
+    ix, iy, KBB = SEM.pressure_boundary_block(P, nx, ny, Lx / nx, Ly / ny, pin=ns._pin)
+    g = iy + (ny * P + 1) * ix
+    assert sorted(g.tolist()) == sorted(np.where(ns._mask_bound & (np.arange(ns.N) != ns._pin))[0].tolist())
+    ref = D[g][:, g].toarray()
+    assert np.abs(KBB - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.linalg.cond(KBB) < 1e8      # the ring block is regular: its inverse is what the device stage applies
