@@ -116,3 +116,16 @@ def test_pressure_boundary_block_matches_oracle(P, nx, ny, Lx, Ly):
     ref = D[g][:, g].toarray()
     assert np.abs(KBB - ref).max() <= 1e-13 * np.abs(ref).max()
     assert np.linalg.cond(KBB) < 1e8      # the ring block is regular: its inverse is what the device stage applies
+
+
+def test_header_is_plain_c():
+    """include/sem_b200.h is the drop-in boundary: it must compile as C99 on its own (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "sem_b200.h")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
