@@ -68,9 +68,11 @@ typedef struct {
     double atol;           /* stop when the true residual 2-norm <= atol */
     int restart;           /* Krylov basis size per cycle */
     int max_iters;         /* total iteration cap */
-    int precond;           /* 0 none, 1 Jacobi, 2 fast diagonalisation (needs sem_ctx_set_fdm); NS: block lower-
-                              triangular with that velocity block; NS only, EXPERIMENTAL: 3 = 2 + block
-                              elimination of the boundary pressure rows (needs sem_ctx_set_pbb) */
+    int precond;           /* 0 none, 1 Jacobi, 2 fast diagonalisation (needs sem_ctx_set_fdm slot 0); NS: block lower-
+                              triangular with that velocity block and the reference's mass preconditioner on the Schur block
+                              (NS:208-212); NS only (need sem_ctx_set_ns_schur): 3 = 2 + block elimination of
+                              the boundary pressure rows, 4 = 3 + two-level Schur preconditioner with a pressure convection-
+                              diffusion stage (needs fdm slots 1 and 2) */
     int verbose;
     /* outputs */
     int iters;             /* operator applications spent */
@@ -90,22 +92,48 @@ long long sem_ctx_vec_len(const sem_ctx *ctx); /* doubles per vec = NX_local*LD 
 /* launch tuning: elements per strip in y and per marching chunk in x (0 = automatic) */
 int sem_ctx_set_tiling(sem_ctx *ctx, int Ty, int Mx);
 
-/* ---- fast-diagonalisation (FDM) preconditioner of the Krylov solvers (sem_krylov.precond = 2) ----------------------
- * Qx: DEVICE, row-major [NX][NX], column k = k-th generalised eigenvector of the assembled 1-D pencil (K1x, M1x) with the
- * Dirichlet end nodes eliminated (their rows, and the unused trailing columns, are zero), normalised Qx^T M1x Qx = I;
- * lamx[NX]: the eigenvalues (1 for unused columns); Qy, lamy likewise for y.  dirichlet_wesn[4]: which sides carry
- * Dirichlet rows.  The arrays are copied.  On a partitioned context (after sem_ctx_attach_comm) Qx is the slab's row range
- * of the GLOBAL matrix, row-major [NX_local][NX_global], lamx[NX_global]; the x transform is then distributed over the ranks
- * (GEMM + ncclReduceScatter, ncclAllGather + GEMM) and the preconditioner stays the exact inverse. */
-int sem_ctx_set_fdm(sem_ctx *ctx, const double *Qx, const double *lamx, const double *Qy, const double *lamy,
-                    const int *dirichlet_wesn);
+/* ---- fast-diagonalisation (FDM) plans: z = (Qx (x) Qy) diag(1/(lx_k + ly_l))^+ (Qx (x) Qy)^T r --------------------------------
+ * Replaces the SuperLU factorisation / solves of NS:178-191 (velocity block) as the preconditioner of the Krylov solvers
+ * (sem_krylov.precond >= 2) and serves the pressure stages of the NS preconditioner.  One direction of a plan: the operator
+ * acts on the nodes [lo, lo + cnt) of the direction; Q^T M1 Q = I, Q^T K1 Q = diag(lam) are the generalised eigenpairs of the
+ * assembled 1-D pencil restricted to those nodes.  fold = 1 (pencil symmetric about the domain centre): Qe [ne][ne] holds the
+ * even eigenvectors on the first ne = ceil(cnt/2) nodes, Qo [no][no] the odd ones on the first no = floor(cnt/2) nodes, lam
+ * the ne even then the no odd eigenvalues -- every transform then costs half the flops.  fold = 0: Qe [cnt][cnt], Qo unused.
+ * All arrays are DEVICE pointers, row-major [node][mode], and are copied.  On a partitioned context the x direction is the
+ * GLOBAL pencil, unfolded: Qe = the slab's rows [NX_local][nmodes] of the global matrix (zero rows at eliminated end nodes),
+ * lam[nmodes], lo / cnt = the lines of the slab the operator acts on; the x transform is then distributed over the ranks
+ * (product + ncclReduceScatter, ncclAllGather + product) and stays the exact inverse.
+ * slot: 0 = Laplacian with the solver's Dirichlet sides (CD operator, NS velocity block), 1 = all-Neumann pressure
+ * Laplacian, 2 = coarse operator of the NS Schur complement.  outside: 1 = z = r outside the node range (identity rows),
+ * 0 = z = 0.  den_floor: denominators <= den_floor are treated as zero modes (pseudo-inverse); < 0 = automatic. */
+typedef struct {
+    int lo, cnt, fold;
+    const double *Qe, *Qo, *lam;
+    int nmodes;            /* partitioned x direction only: number of global modes */
+} sem_fdm_dir;
+int sem_ctx_set_fdm(sem_ctx *ctx, int slot, const sem_fdm_dir *x, const sem_fdm_dir *y, int outside, double den_floor);
+/* z = plan(r) for nf (1 or 2) consecutive vecs; r and z may alias */
+int sem_fdm_apply(sem_ctx *ctx, int slot, const double *r, double *z, int nf, void *stream);
 
-/* EXPERIMENTAL (written at the end of round 1, compiled but not yet validated on a GPU; nothing uses it unless
- * sem_krylov.precond == 3): boundary block of the NS pressure rows.  idx_host[nb]: offsets ix*LD + iy of the boundary pressure
- * nodes (the pin node left out); inv_dev: DEVICE, row-major nb x nb inverse of the stiffness matrix restricted to those nodes
- * (rows K[mask,:] of NS:119,157).  The NS preconditioner then solves the boundary rows exactly, z_B = K_BB^-1 (r_B - K_BI z_I),
- * instead of scaling them by 1/M.  One GPU only.  The arrays are copied. */
-int sem_ctx_set_pbb(sem_ctx *ctx, const long long *idx_host, int nb, const double *inv_dev);
+/* ---- Schur-complement stages of the NS preconditioner (sem_krylov.precond = 3, 4); replaces the diagonal-mass
+ * preconditioner of NS:208-212.  All arrays are HOST pointers and are copied.
+ *   wl, wr [P+1]        element-local values (1 - xn_j) L_P(xi_j), xn_j L_P(xi_j) of the coarse-space functions
+ *   ta/tinv/tcp_x [N_ex+1], _y [N_ey+1]   Thomas factors of the tridiagonal Gram matrices W^T M W of the two directions
+ *   lfx [NX_global], lfy [NY]             1-D factors of the pressure part l_c = lfx (x) lfy of the Jacobian's left null vector
+ *   singular            the Jacobian is singular (l_c vanishes on the boundary and at the pin): apply the member correction
+ *   inv_den             1 / (m_c . l_c), m_c = M_p l_c
+ *   two_level           0: only the ring elimination is available (level 4 falls back to 3)
+ *   cheb_lo, cheb_hi, cheb_steps           spectrum bounds of the diagonally scaled ring block and polynomial degree */
+typedef struct {
+    const double *wl, *wr;
+    const double *ta_x, *tinv_x, *tcp_x, *ta_y, *tinv_y, *tcp_y;
+    const double *lfx, *lfy;
+    int singular, two_level;
+    double inv_den;
+    double cheb_lo, cheb_hi;
+    int cheb_steps;
+} sem_ns_schur_desc;
+int sem_ctx_set_ns_schur(sem_ctx *ctx, const sem_ns_schur_desc *desc);
 
 /* ---- multi-GPU: one process per GPU, element columns [m_begin, m_end) per rank (sem_mesh_desc).  Rank 0 creates a
  * 128-byte NCCL unique id, the caller distributes it (torch.distributed), every rank attaches.  Afterwards every operator
@@ -165,6 +193,11 @@ int sem_ns_jvp(sem_ctx *ctx, const sem_ns_state *st, const double *du, const dou
 long long sem_ns_work_len(const sem_ctx *ctx, int restart);
 int sem_ns_solve(sem_ctx *ctx, const sem_ns_state *st, const double *rhs3, double *x3, sem_krylov *kr,
                  double *work, long long work_len, void *stream);
+
+/* One application of the NS preconditioner (what = 0: z3 = P^-1 r3 at `level`) or of one of its stages (1 coarse, 2 ring
+ * elimination, 3 Stokes-Schur residual, 4 pressure convection-diffusion) -- for the stage-by-stage parity tests. */
+int sem_ns_precond_debug(sem_ctx *ctx, const sem_ns_state *st, int what, int level, const double *in, const double *in2,
+                         double *out, void *stream);
 
 /* ---- reductions used by the Python layer (deterministic two-stage sums) ---------------------------------------- */
 /* n = (number of fields) * sem_ctx_vec_len(); interface lines are counted once and the sum is global over ranks */

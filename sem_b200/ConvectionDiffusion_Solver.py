@@ -111,10 +111,18 @@ class ConvectionDiffusionSolver:
                        "sem_cd_solve")
         self.last_iters, self.last_resnorm = kr.iters, kr.resnorm
         if code != 0:
-            raise RuntimeError(f'ConvectionDiffusion GMRES: Failed to converge in {kr.iters} iterations')
-        if 'LGMRES_suc' in self._iprint:
-            print(f'ConvectionDiffusion GMRES: Converged in {kr.iters} evaluations with 2-norm {kr.resnorm}')
+            raise RuntimeError(f'ConvectionDiffusion LGMRES: Failed to converge in {kr.iters} iterations')   # text of CD:150
+        if 'LGMRES_suc' in self._iprint:                                                                     # text of CD:152-154
+            print(f'ConvectionDiffusion LGMRES: Converged in {kr.iters} evaluations with max-norm {self._residual_maxnorm(rhs, x)}')
         return x
+
+    def _residual_maxnorm(self, rhs, x):
+        """max-norm of J x - rhs, the number the reference prints on success (CD:153); only evaluated for 'LGMRES_suc'."""
+        d = self._dev
+        st = self._state(with_jac=False)
+        r = d.zeros()
+        L.check(self._lib.sem_cd_jvp(d.ctx, C.byref(st), x.data_ptr(), None, None, r.data_ptr(), d.stream), "sem_cd_jvp")
+        return float((r - rhs).abs().max())
 
     # ---- reference API -----------------------------------------------------------------------------------------------------
     def _get_residuals(self, T: np.ndarray, u: np.ndarray, v: np.ndarray) -> np.ndarray:

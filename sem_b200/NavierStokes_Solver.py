@@ -26,8 +26,10 @@ class NavierStokesSolver:
                  mtol=1e-7, mtol_newton=1e-5, iprint: list = ['NEWTON_suc', 'NEWTON_iter'],
                  device: int = None, restart: int = None, max_newton: int = 50, partition=None, precond: str = 'auto'):
         """Arguments as NS:11-41.  Extra, optional: ``device``, ``restart`` (Krylov basis size), ``max_newton``,
-        ``precond`` of the velocity block ('auto' | 'fdm' | 'jacobi'; auto = fast diagonalisation on one GPU;
-        'fdm+bb' = experimental, see ``_krylov``)."""
+        ``precond`` ('auto' | 'full' | 'fdm+bb' | 'fdm' | 'jacobi'): 'jacobi' / 'fdm' = Jacobi / fast-diagonalisation velocity
+        block with the reference's diagonal-mass Schur preconditioner (NS:208-212); 'fdm+bb' adds the block elimination of the
+        pressure-Neumann boundary rows; 'full' (= 'auto') the two-level Schur preconditioner with a pressure convection-
+        diffusion stage on top."""
         self._iprint = iprint
         self._Re = Re
         self._Gr = Gr
@@ -58,8 +60,8 @@ class NavierStokesSolver:
         self._x = d.zeros(3)
         self._restart = restart
         if precond == 'auto':
-            precond = 'fdm'
-        self._precond = {'jacobi': 1, 'fdm': 2, 'fdm+bb': 3}[precond]   # 'fdm+bb': experimental, see _krylov
+            precond = 'full'
+        self._precond = {'jacobi': 1, 'fdm': 2, 'fdm+bb': 3, 'full': 4}[precond]
         self._work = None
         self.last_iters = 0
         self.last_resnorm = float('nan')
@@ -121,13 +123,10 @@ class NavierStokesSolver:
         kr.atol = float(self._mtol * np.sqrt(self.N))            # NS:223
         kr.restart = self._restart
         kr.max_iters = max(2000, 10 * self._restart)
-        if self._precond in (2, 3) and not self._dev.has_fdm:
+        if self._precond >= 2 and not self._dev.has_fdm:
             self._dev.setup_fdm([1, 1, 1, 1])                    # velocity Dirichlet rows on all four sides (NS:78-88)
-        if self._precond == 3 and not self._dev.has_pbb:
-            # EXPERIMENTAL, opt-in (precond='fdm+bb'), not validated on a GPU in round 1: block elimination of the
-            # pressure-Neumann boundary rows in the preconditioner (3.5x fewer iterations in the CPU
-            # study, same member of the solution set)
-            self._dev.setup_pressure_boundary_block(int(self.N / 2))
+        if self._precond >= 3 and not self._dev.has_ns_schur:
+            self._dev.setup_ns_schur(int(self.N / 2))            # pin node int(N/2), NS:89
         kr.precond = self._precond
         kr.verbose = 2 if 'LGMRES_iter' in self._iprint else 0
         return kr
@@ -143,10 +142,45 @@ class NavierStokesSolver:
         self.last_iters, self.last_resnorm = kr.iters, kr.resnorm
         self.krylov_iters.append(kr.iters)
         if code != 0:
-            raise RuntimeError(f'NavierStokes GMRES: Failed to converge in {kr.iters} iterations')
-        if 'LGMRES_suc' in self._iprint:
-            print(f'NavierStokes GMRES: Converged in {kr.iters} evaluations with 2-norm {kr.resnorm}')
+            raise RuntimeError(f'NavierStokes LGMRES: Failed to converge in {kr.iters} iterations')   # text of NS:226
+        if 'LGMRES_suc' in self._iprint:                                                              # text of NS:228-230
+            print(f'NavierStokes LGMRES: Converged in {kr.iters} evaluations with max-norm {self._residual_maxnorm(rhs3, x3)}')
         return x3
+
+    def _residual_maxnorm(self, rhs3, x3):
+        """max-norm of J x - rhs over the three fields (the reference prints the max-norm of its Schur residual, NS:229);
+        only evaluated for 'LGMRES_suc'."""
+        d = self._dev
+        st = self._state()
+        r = d.zeros(3)
+        L.check(self._lib.sem_ns_jvp(d.ctx, C.byref(st), x3[0].data_ptr(), x3[1].data_ptr(), x3[2].data_ptr(), None,
+                                     r[0].data_ptr(), r[1].data_ptr(), r[2].data_ptr(), d.stream), "sem_ns_jvp")
+        return float((r - rhs3).abs().max())
+
+    def _precond_debug(self, what, level, a, b=None):
+        """One application of the preconditioner (what = 0: a = (r_u, r_v, r_c) -> (z_u, z_v, z_p) at ``level``) or of one of
+        its Schur stages (1 coarse(a), 2 ring elimination of b for right-hand side a, 3 a - S_0 b, 4 pcd(a)); numpy in / out.
+        For the stage-by-stage parity tests against oracle/ns_precond.py.  Not part of the reference API."""
+        d = self._dev
+        if not (self._have_sys and self._have_jac):
+            raise RuntimeError('NavierStokes: _get_residuals and _calc_jacobians must precede the preconditioner')
+        self._precond, keep = max(self._precond, level), self._precond
+        self._krylov()
+        self._precond = keep
+        st = self._state()
+        if what == 0:
+            for k in range(3):
+                d.to_device(a[k], self._out[k])
+            L.check(self._lib.sem_ns_precond_debug(d.ctx, C.byref(st), 0, int(level), self._out.data_ptr(), None,
+                                                   self._x.data_ptr(), d.stream), "sem_ns_precond_debug")
+            return tuple(d.to_host(self._x[k]) for k in range(3))
+        d.to_device(a, self._in[0])
+        if b is not None:
+            d.to_device(b, self._in[1])
+        L.check(self._lib.sem_ns_precond_debug(d.ctx, C.byref(st), int(what), int(level), self._in[0].data_ptr(),
+                                               self._in[1].data_ptr() if b is not None else None,
+                                               self._in[2].data_ptr(), d.stream), "sem_ns_precond_debug")
+        return d.to_host(self._in[2])
 
     def _spectral_norm(self, r3):
         """2-norm of the 3 x N residual array as a MATRIX (largest singular value) -- what

@@ -211,3 +211,57 @@ def pressure_boundary_block(P: int, N_ex: int, N_ey: int, dx: float, dy: float, 
     same_y = iy[:, None] == iy[None, :]
     KBB = K1x[ix[:, None], ix[None, :]] * (M1y[iy][:, None] * same_y) + (M1x[ix][:, None] * same_x) * K1y[iy[:, None], iy[None, :]]
     return ix, iy, KBB
+
+
+def ring_chebyshev_parameters(P: int, N_ex: int, N_ey: int, dx: float, dy: float, pin: int = None, target: float = 0.03,
+                              max_steps: int = 8):
+    """Spectrum bounds ``(lo, hi)`` of the diagonally scaled boundary-ring block ``D^-1/2 K_BB D^-1/2`` of the pressure rows
+    (rows K[mask,:] of NS:119,157, pin node left out) and the degree of the fixed Chebyshev polynomial that replaces its inverse
+    in the NS preconditioner: the smallest degree whose error bound ``2 r^k / (1 + r^2k)``, ``r = (sqrt(hi/lo) - 1) /
+    (sqrt(hi/lo) + 1)``, is below ``target`` (3 for square elements, where the spectrum lies in about [0.56, 1.50] for every
+    mesh and order), at most ``max_steps``.  The block is assembled sparsely on the host from the 1-D matrices (O(ring P)
+    entries) and its extreme eigenvalues come from Lanczos; a 2 % margin is added on both sides."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    NX, NY = N_ex * P + 1, N_ey * P + 1
+    Ks, w = GLL.standard_stiffness_matrix(P), GLL.standard_nodes(P)[1]
+
+    def line(A_s, N_e):
+        n = A_s.shape[0]
+        ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing='ij')
+        rows = np.concatenate([(ii + m * P).ravel() for m in range(N_e)])
+        cols = np.concatenate([(jj + m * P).ravel() for m in range(N_e)])
+        return sps.coo_matrix((np.tile(A_s.ravel(), N_e), (rows, cols)), shape=(N_e * P + 1,) * 2).tocsr()
+
+    K1x, K1y = line(2.0 / dx * Ks, N_ex), line(2.0 / dy * Ks, N_ey)
+    M1x, M1y = line(dx / 2.0 * np.diag(w), N_ex).diagonal(), line(dy / 2.0 * np.diag(w), N_ey).diagonal()
+    ix = np.concatenate([np.zeros(NY, int), np.full(NY, NX - 1), np.repeat(np.arange(1, NX - 1), 2)])
+    iy = np.concatenate([np.arange(NY), np.arange(NY), np.tile([0, NY - 1], NX - 2)])
+    if pin is not None:
+        keep = (iy + NY * ix) != pin
+        ix, iy = ix[keep], iy[keep]
+    nb = ix.size
+    # selection matrices ring <- x line / y line; K_BB = sum over the y values {0, NY-1, ...} ... assembled through the masks
+    Sx = sps.csr_matrix((np.ones(nb), (np.arange(nb), ix)), shape=(nb, NX))
+    Sy = sps.csr_matrix((np.ones(nb), (np.arange(nb), iy)), shape=(nb, NY))
+    same_y = (Sy @ Sy.T).tocsr()                       # 1 where two ring nodes share iy
+    same_x = (Sx @ Sx.T).tocsr()
+    A = (Sx @ K1x @ Sx.T).multiply(same_y).multiply(sps.csr_matrix(M1y[iy][:, None])) \
+        + (Sy @ K1y @ Sy.T).multiply(same_x).multiply(sps.csr_matrix(M1x[ix][:, None]))
+    A = sps.csr_matrix(A)
+    sd = 1.0 / np.sqrt(A.diagonal())
+    B = sps.diags(sd) @ A @ sps.diags(sd)
+    B = 0.5 * (B + B.T)
+    if nb <= 400:
+        ev = np.linalg.eigvalsh(B.toarray())
+        lo, hi = ev[0], ev[-1]
+    else:
+        v0 = np.cos(np.arange(nb) * 0.7) + 1.5          # fixed start vector: reproducible bounds
+        hi = spla.eigsh(B, k=1, which='LA', v0=v0, tol=1e-10, return_eigenvectors=False)[0]
+        lo = spla.eigsh(B, k=1, which='SA', v0=v0, tol=1e-10, return_eigenvectors=False)[0]
+    lo, hi = 0.98 * float(lo), 1.02 * float(hi)
+    r = (np.sqrt(hi / lo) - 1.0) / (np.sqrt(hi / lo) + 1.0)
+    steps = 1
+    while steps < max_steps and 2.0 * r ** steps / (1.0 + r ** (2 * steps)) > target:
+        steps += 1
+    return lo, hi, steps

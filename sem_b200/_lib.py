@@ -38,6 +38,19 @@ class sem_ns_state(C.Structure):
                 ("v", C.c_void_p), ("gxu", C.c_void_p), ("gyu", C.c_void_p), ("gxv", C.c_void_p), ("gyv", C.c_void_p)]
 
 
+class sem_fdm_dir(C.Structure):
+    _fields_ = [("lo", C.c_int), ("cnt", C.c_int), ("fold", C.c_int), ("Qe", C.c_void_p), ("Qo", C.c_void_p),
+                ("lam", C.c_void_p), ("nmodes", C.c_int)]
+
+
+class sem_ns_schur_desc(C.Structure):
+    _fields_ = [("wl", C.c_void_p), ("wr", C.c_void_p),
+                ("ta_x", C.c_void_p), ("tinv_x", C.c_void_p), ("tcp_x", C.c_void_p),
+                ("ta_y", C.c_void_p), ("tinv_y", C.c_void_p), ("tcp_y", C.c_void_p),
+                ("lfx", C.c_void_p), ("lfy", C.c_void_p), ("singular", C.c_int), ("two_level", C.c_int),
+                ("inv_den", C.c_double), ("cheb_lo", C.c_double), ("cheb_hi", C.c_double), ("cheb_steps", C.c_int)]
+
+
 class sem_krylov(C.Structure):
     _fields_ = [("atol", C.c_double), ("restart", C.c_int), ("max_iters", C.c_int), ("precond", C.c_int),
                 ("verbose", C.c_int), ("iters", C.c_int), ("resnorm", C.c_double)]
@@ -59,7 +72,6 @@ SIGNATURES = {
     "sem_nccl_unique_id": (C.c_int, [_P]),
     "sem_ctx_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "sem_ctx_comm_mode": (C.c_int, [_P]),
-    "sem_ctx_set_pbb": (C.c_int, [_P, _P, C.c_int, _P]),
     "sem_h2d": (C.c_int, [_P, _P, _P, _P]),
     "sem_d2h": (C.c_int, [_P, _P, _P, _P]),
     "sem_apply_stiffness": (C.c_int, [_P, _P, _P, _P]),
@@ -71,7 +83,10 @@ SIGNATURES = {
     "sem_cd_residual": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P]),
     "sem_cd_jacobians": (C.c_int, [_P, C.c_double, _P, _P, _P, _P]),
     "sem_cd_jvp": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P, _P, _P]),
-    "sem_ctx_set_fdm": (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(C.c_int)]),
+    "sem_ctx_set_fdm": (C.c_int, [_P, C.c_int, C.POINTER(sem_fdm_dir), C.POINTER(sem_fdm_dir), C.c_int, C.c_double]),
+    "sem_fdm_apply": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
+    "sem_ctx_set_ns_schur": (C.c_int, [_P, C.POINTER(sem_ns_schur_desc)]),
+    "sem_ns_precond_debug": (C.c_int, [_P, C.POINTER(sem_ns_state), C.c_int, C.c_int, _P, _P, _P, _P]),
     "sem_cd_jvp_host": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P, _P, _P]),
     "sem_cd_work_len": (_LL, [_P, C.c_int]),
     "sem_cd_solve": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, C.POINTER(sem_krylov), _P, _LL, _P]),

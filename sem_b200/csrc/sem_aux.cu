@@ -500,96 +500,12 @@ int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Boundary block of the NS pressure rows (experimental, sem_ctx_set_pbb): gather / scatter of the boundary pressure nodes
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void k_pbb_zero(double* __restrict__ z, const long long* __restrict__ idx, int nb) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < nb) z[idx[a]] = 0.0;
+__global__ void k_sub(const double* a, const double* b, double* out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] - b[i];
 }
-__global__ void k_pbb_gather(const double* __restrict__ r, const double* __restrict__ q, const long long* __restrict__ idx,
-                             int nb, double* __restrict__ rhs) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < nb) rhs[a] = r[idx[a]] - q[idx[a]];
-}
-__global__ void k_pbb_scatter(const double* __restrict__ zb, const long long* __restrict__ idx, int nb,
-                              double* __restrict__ z) {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < nb) z[idx[a]] = zb[a];
-}
-
-int aux_pbb_zero(double* z, const long long* idx, int nb, cudaStream_t st) {
-    k_pbb_zero<<<(nb + 255) / 256, 256, 0, st>>>(z, idx, nb);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
-}
-int aux_pbb_gather(const double* r, const double* q, const long long* idx, int nb, double* rhs, cudaStream_t st) {
-    k_pbb_gather<<<(nb + 255) / 256, 256, 0, st>>>(r, q, idx, nb, rhs);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
-}
-int aux_pbb_scatter(const double* zb, const long long* idx, int nb, double* z, cudaStream_t st) {
-    k_pbb_scatter<<<(nb + 255) / 256, 256, 0, st>>>(zb, idx, nb, z);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// fast-diagonalisation preconditioner: spectral scaling and Dirichlet pass-through
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void k_fdm_scale(const MeshDev g, const double* __restrict__ lx, const double* __restrict__ ly,
-                            double* __restrict__ z, int rows, double floor_, long long batch_stride) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tot = (long long)rows * g.LD;
-    if (idx >= tot) return;
-    const int ix = (int)(idx / g.LD), iy = (int)(idx % g.LD);
-    if (iy >= g.NY) return;
-    const double den = lx[ix] + ly[iy];
-    double* zb = z + (long long)blockIdx.y * batch_stride;
-    // the constant mode of an all-Neumann Laplacian has lx + ly = 0: pseudo-inverse
-    zb[idx] = (den > floor_) ? zb[idx] / den : 0.0;
-}
-
-// z[i][j] /= lx[i] + ly[j] for the `rows` spectral rows of z (lx already offset to the first of them); `batch` fields
-// `batch_stride` doubles apart
-int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, int rows, cudaStream_t st, int batch,
-                  long long batch_stride) {
-    const long long tot = (long long)rows * g.LD;
-    if (tot <= 0) return 0;
-    // lx + ly = 0 only for the constant mode of an all-Neumann problem; the largest eigenvalue is ~ P^4 (1/dx^2 + 1/dy^2)
-    // and the eigen-solver's absolute error ~ 1e-16 of that
-    const double p4 = (double)g.P * g.P * g.P * g.P;
-    const double floor_ = 1e-13 * p4 * (1.0 / (g.dx * g.dx) + 1.0 / (g.dy * g.dy));
-    k_fdm_scale<<<dim3((unsigned)((tot + 255) / 256), (unsigned)batch), 256, 0, st>>>(g, lx, ly, z, rows, floor_, batch_stride);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
-}
-
-struct DirFlags { int d[4]; };
-
-// boundary nodes only: threads 0..NY-1 -> line 0, NY..2NY-1 -> last line, then the first / last column of every line.
-// Dirichlet sides (global W / E lines live on the first / last rank only): z = r, the identity rows of the operator.
-__global__ void k_fdm_boundary(const MeshDev g, const DirFlags f, const double* __restrict__ r, double* __restrict__ z,
-                               long long batch_stride) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int ix, iy;
-    if (t < g.NY) { ix = 0; iy = t; }
-    else if (t < 2 * g.NY) { ix = g.NX - 1; iy = t - g.NY; }
-    else if (t < 2 * g.NY + g.NX) { ix = t - 2 * g.NY; iy = 0; }
-    else if (t < 2 * g.NY + 2 * g.NX) { ix = t - 2 * g.NY - g.NX; iy = g.NY - 1; }
-    else return;
-    const bool dir = (ix == 0 && !g.has_left && f.d[SIDE_W]) || (ix == g.NX - 1 && !g.has_right && f.d[SIDE_E]) ||
-                     (iy == 0 && f.d[SIDE_S]) || (iy == g.NY - 1 && f.d[SIDE_N]);
-    const long long o = (long long)blockIdx.y * batch_stride + (long long)ix * g.LD + iy;
-    if (dir) z[o] = r[o];
-}
-
-int aux_fdm_boundary(const MeshDev& g, const int* dir_wesn, const double* r, double* z, cudaStream_t st, int batch,
-                     long long batch_stride) {
-    DirFlags f;
-    for (int k = 0; k < 4; ++k) f.d[k] = dir_wesn[k];
-    const int tot = 2 * (g.NX + g.NY);
-    k_fdm_boundary<<<dim3((unsigned)((tot + 255) / 256), (unsigned)batch), 256, 0, st>>>(g, f, r, z, batch_stride);
+int aux_sub(const double* a, const double* b, double* out, long long n, cudaStream_t st) {
+    k_sub<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, out, n);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -71,17 +71,7 @@ int aux_ns_jacobi(const MeshDev& g, const double* dK, const double* gxu, const d
 int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double* div, double* zp, int pin_gx,
                       int pin_iy, cudaStream_t st);
 
-// ---- boundary block of the NS pressure rows (experimental, sem_ctx_set_pbb): idx = offsets of the boundary nodes ------
-int aux_pbb_zero(double* z, const long long* idx, int nb, cudaStream_t st);                                  // z[idx] = 0
-int aux_pbb_gather(const double* r, const double* q, const long long* idx, int nb, double* rhs, cudaStream_t st);   // rhs = (r - q)[idx]
-int aux_pbb_scatter(const double* zb, const long long* idx, int nb, double* z, cudaStream_t st);             // z[idx] = zb
-
-// ---- fast-diagonalisation preconditioner pieces (see sem_capi.cu) ---------------------------------------------------
-// z[i][iy] /= lx[i] + ly[iy] for `rows` spectral rows (0 for the constant mode of an all-Neumann problem)
-int aux_fdm_scale(const MeshDev& g, const double* lx, const double* ly, double* z, int rows, cudaStream_t st, int batch = 1,
-                  long long batch_stride = 0);
-// z = r on the nodes of the Dirichlet sides (W, E, S, N flags)
-int aux_fdm_boundary(const MeshDev& g, const int* dir_wesn, const double* r, double* z, cudaStream_t st, int batch = 1,
-                     long long batch_stride = 0);
+// out = a - b
+int aux_sub(const double* a, const double* b, double* out, long long n, cudaStream_t st);
 
 }  // namespace semb

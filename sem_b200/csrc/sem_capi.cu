@@ -5,8 +5,9 @@
 #include "sem_dispatch.h"
 #include "sem_march.cuh"
 #include "sem_march3.cuh"
+#include "sem_gemm.cuh"
+#include "sem_schur.cuh"
 #include <cstdlib>
-#include <cublas_v2.h>
 
 #include <cmath>
 #include <algorithm>
@@ -36,6 +37,8 @@ static const struct {
     size_t (*smem3)(int);
 } g_orders[SEM_MAX_P] = {SEM_FOR_EACH_P(SEM_TAB_ENTRY)};
 
+#define SEM_FDM_SLOTS 3
+enum { SEM_FDM_MAIN = 0, SEM_FDM_NEUMANN = 1, SEM_FDM_COARSE = 2 };
 #define SEM_HOST_SEGMENTS 32  // most element-column segments of the host-buffer pipeline (default 16, SEM_B200_HOST_SEGMENTS)
 #define SEM_GMRES_LAG 6       // Arnoldi steps enqueued ahead of the host-side Givens / convergence test
 
@@ -69,20 +72,55 @@ struct sem_ctx {
     double* dStageOut;
     cudaEvent_t ev_up[SEM_HOST_SEGMENTS], ev_done[SEM_HOST_SEGMENTS], ev_start, ev_end;
     int streams_ready;
-    // fast-diagonalisation preconditioner (sem_ctx_set_fdm): 1-D generalised eigenpairs of the x and y pencils
-    cublasHandle_t blas;
-    void* blas_ws;
-    double *fQx, *fLx, *fQy, *fLy, *fT1, *fT2;
-    double *fB1, *fB2;        // two-field transform buffers of the batched apply (allocated on first use)
-    // boundary block of the NS pressure rows (sem_ctx_set_pbb, experimental): offsets of the boundary pressure nodes, the
-    // dense inverse of K restricted to them (row-major nb x nb), gathered right-hand side and solution
-    long long* pbb_idx;
-    double *pbb_inv, *pbb_rhs, *pbb_z;
-    int pbb_n;
-    int fdm_ready, fdm_dir[4];
-    int fdm_nxg, fdm_block;  // partitioned mesh: global line count and spectral modes per rank (exact distributed FDM)
+    // fast-diagonalisation plans (sem_ctx_set_fdm), see sem_gemm.cuh.  Slots: SEM_FDM_MAIN the Laplacian with the solver's
+    // Dirichlet sides (CD operator / NS velocity block), SEM_FDM_NEUMANN the all-Neumann pressure Laplacian (pseudo-inverse),
+    // SEM_FDM_COARSE the structured coarse operator of the NS Schur complement.  One GPU: FdmPlan; partitioned: FdmDist.
+    FdmPlan plan[SEM_FDM_SLOTS];
+    struct FdmDist {
+        int ready, outside;
+        int nmodes, B, modesP;     // global x modes, modes per rank (multiple of 128), B * world
+        int s1, k1, k1p;           // lines [s1, s1 + k1) of the slab enter the forward transform (k1p: padded to 16)
+        int s4, m4, m4p;           // lines [s4, s4 + m4) of the slab are produced by the backward transform (m4p: padded to 128)
+        double *QxT, *Qx, *lamx;   // [modesP][k1p], [m4p][modesP], [modesP]
+        FdmDir y;
+        int cols;
+        double *R, *T, *mA, *mB, *X;
+        double den_floor;
+    } dist[SEM_FDM_SLOTS];
+    // Navier-Stokes Schur-complement preconditioner (sem_ctx_set_ns_schur): projector tables, null-vector factors, work vectors
+    struct NsSchur {
+        int ready, singular, two_level;
+        double inv_den;                  // 1 / (m_c . l_c)
+        int cheb_steps;
+        double cheb_inv_theta, cheb_a[8], cheb_b[8];
+        PwDir px, py;
+        double* tables;                  // one device block holding wl, wr and the Thomas factors of both directions
+        double *lc, *mc;                 // l_c = lfx (x) lfy and m_c = M_p l_c as vectors
+        double* w[10];                   // work vectors (zero initialised): Y, Z1, R1, G0, G1, V0, V1, NR, RHO, E
+        double *cx, *cy;                 // projector coefficients: [(N_ex + 1)][LD] and [NX][ldcy]
+        int ldcy;
+        double* sums;                    // device [2]
+    } sch;
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
 };
+
+static void schur_free(sem_ctx::NsSchur& q) {
+    if (q.tables) cudaFree(q.tables);
+    if (q.lc) cudaFree(q.lc);
+    if (q.mc) cudaFree(q.mc);
+    for (double* p : q.w)
+        if (p) cudaFree(p);
+    if (q.cx) cudaFree(q.cx);
+    if (q.cy) cudaFree(q.cy);
+    if (q.sums) cudaFree(q.sums);
+    std::memset(&q, 0, sizeof(q));
+}
+
+static void fdm_dist_free(sem_ctx::FdmDist& d) {
+    if (d.QxT) { cudaFree(d.QxT); cudaFree(d.Qx); cudaFree(d.lamx); cudaFree(d.R); cudaFree(d.T); cudaFree(d.mA); cudaFree(d.mB); cudaFree(d.X); }
+    fdm_dir_free(d.y);
+    std::memset(&d, 0, sizeof(d));
+}
 
 #define SEM_CHECK_CTX(ctx)                              \
     do {                                                \
@@ -170,10 +208,11 @@ extern "C" void sem_ctx_destroy(sem_ctx* c) {
         if (e.exec) cudaGraphExecDestroy(e.exec);
     if (c->has_comm) comm_destroy(c->comm);
     if (c->dStageOut) cudaFree(c->dStageOut);
-    if (c->fQx) { cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2); }
-    if (c->fB1) { cudaFree(c->fB1); cudaFree(c->fB2); }
-    if (c->pbb_idx) { cudaFree(c->pbb_idx); cudaFree(c->pbb_inv); cudaFree(c->pbb_rhs); cudaFree(c->pbb_z); }
-    if (c->blas) { cublasDestroy(c->blas); cudaFree(c->blas_ws); }
+    for (int k = 0; k < SEM_FDM_SLOTS; ++k) {
+        fdm_plan_free(c->plan[k]);
+        fdm_dist_free(c->dist[k]);
+    }
+    schur_free(c->sch);
     if (c->streams_ready) {
         cudaStreamDestroy(c->s_side); cudaStreamDestroy(c->s_side2); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h); cudaStreamDestroy(c->s_solve); cudaStreamDestroy(c->s_main);
         cudaEventDestroy(c->ev_g0); cudaEventDestroy(c->ev_g1);
@@ -668,167 +707,357 @@ extern "C" int sem_axpby(sem_ctx* c, double a, const double* x, double b, double
 // the assembled stiffness matrix is a Kronecker sum of 1-D operators, K = K1x (x) M1y + M1x (x) K1y, and every side is
 // either all Dirichlet or all Neumann, so the Laplacian with the Dirichlet rows eliminated is inverted exactly by the
 // generalised eigenpairs of the two 1-D pencils:   K^-1 = (Qx (x) Qy) diag(1/(lx_i + ly_j)) (Qx (x) Qy)^T,
-// Q^T M1 Q = I, Q^T K1 Q = diag(l).  Four dense fp64 GEMMs (cuBLAS: plain library GEMMs on the tensor cores) + one
-// scaling pass per application; the iteration count of the Krylov solver no longer grows with the mesh.
-// Q is stored row-major [n][n] with zero rows at Dirichlet end nodes, so the result is zero there and the identity rows
-// of the operator are restored by a boundary pass (z = r).
+// Q^T M1 Q = I, Q^T K1 Q = diag(l).  The four transforms are dense fp64 products on the DMMA kernel of sem_gemm.cu; a
+// direction whose pencil is symmetric about the domain centre (both ends Dirichlet or both Neumann) is folded into an even
+// and an odd half-size product (half the flops); the spectral scaling is the epilogue of the second product.
 // ---------------------------------------------------------------------------------------------------------------
-#define SEM_CUBLAS(call)                                                                                   \
-    do {                                                                                                   \
-        cublasStatus_t _s = (call);                                                                        \
-        if (_s != CUBLAS_STATUS_SUCCESS) {                                                                 \
-            set_error(std::string(#call) + " failed with cuBLAS status " + std::to_string((int)_s));      \
-            return -1;                                                                                     \
-        }                                                                                                  \
-    } while (0)
+__global__ void k_pad_rows(const double* __restrict__ src, int src_ld, int row0, int nrows, int ncols, double* __restrict__ dst,
+                           int dst_ld, int transpose) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (i >= nrows || j >= ncols) return;
+    const double v = src[(size_t)(row0 + i) * src_ld + j];
+    if (transpose) dst[(size_t)j * dst_ld + i] = v;
+    else dst[(size_t)i * dst_ld + j] = v;
+}
 
-extern "C" int sem_ctx_set_fdm(sem_ctx* c, const double* Qx, const double* lamx, const double* Qy, const double* lamy,
-                               const int* dirichlet_wesn) {
+static double fdm_den_floor(const MeshDev& g) {
+    // lx + ly = 0 only for the constant mode of an all-Neumann problem; the largest eigenvalue is ~ P^4 (1/dx^2 + 1/dy^2)
+    // and the eigen-solver's absolute error ~ 1e-16 of that
+    const double p4 = (double)g.P * g.P * g.P * g.P;
+    return 1e-13 * p4 * (1.0 / (g.dx * g.dx) + 1.0 / (g.dy * g.dy));
+}
+
+extern "C" int sem_ctx_set_fdm(sem_ctx* c, int slot, const sem_fdm_dir* x, const sem_fdm_dir* y, int outside, double den_floor) {
     SEM_CHECK_CTX(c);
-    const size_t nx = (size_t)c->g.NX, ny = (size_t)c->g.NY, ld = (size_t)c->g.LD;
-    const size_t nxg = (size_t)c->g.NXg;                       // == nx on one GPU
-    const int world = c->has_comm ? c->comm.world : 1;
+    if (slot < 0 || slot >= SEM_FDM_SLOTS || !x || !y) { set_error("sem_ctx_set_fdm: bad slot / null direction"); return -2; }
     if (!c->has_comm && (c->g.has_left || c->g.has_right)) {
         set_error("sem_ctx_set_fdm: a partitioned context needs its communicator first (sem_ctx_attach_comm)");
         return -2;
     }
-    const size_t block = (nxg + world - 1) / world;            // spectral modes per rank
-    const size_t t_rows = (world > 1) ? block * world : nx;    // rows of the transform buffers
-    if (c->fQx) {
-        cudaFree(c->fQx); cudaFree(c->fLx); cudaFree(c->fQy); cudaFree(c->fLy); cudaFree(c->fT1); cudaFree(c->fT2);
-        c->fQx = nullptr;
-    }
-    SEM_CUDA(cudaMalloc(&c->fQx, sizeof(double) * nx * nxg));
-    SEM_CUDA(cudaMalloc(&c->fLx, sizeof(double) * t_rows));
-    SEM_CUDA(cudaMalloc(&c->fQy, sizeof(double) * ny * ny));
-    SEM_CUDA(cudaMalloc(&c->fLy, sizeof(double) * ny));
-    SEM_CUDA(cudaMalloc(&c->fT1, sizeof(double) * t_rows * ld));
-    SEM_CUDA(cudaMalloc(&c->fT2, sizeof(double) * t_rows * ld));
-    SEM_CUDA(cudaMemset(c->fT1, 0, sizeof(double) * t_rows * ld));   // the GEMMs never touch the pad columns
-    SEM_CUDA(cudaMemset(c->fT2, 0, sizeof(double) * t_rows * ld));
-    if (!c->blas) {
-        SEM_CUBLAS(cublasCreate(&c->blas));
-        SEM_CUDA(cudaMalloc(&c->blas_ws, (size_t)32 << 20));   // fixed workspace: the GEMMs are captured into CUDA graphs
-        SEM_CUBLAS(cublasSetWorkspace(c->blas, c->blas_ws, (size_t)32 << 20));
-    }
-    SEM_CUDA(cudaMemcpy(c->fQx, Qx, sizeof(double) * nx * nxg, cudaMemcpyDeviceToDevice));
-    SEM_CUDA(cudaMemset(c->fLx, 0, sizeof(double) * t_rows));
-    SEM_CUDA(cudaMemcpy(c->fLx, lamx, sizeof(double) * nxg, cudaMemcpyDeviceToDevice));
-    SEM_CUDA(cudaMemcpy(c->fQy, Qy, sizeof(double) * ny * ny, cudaMemcpyDeviceToDevice));
-    SEM_CUDA(cudaMemcpy(c->fLy, lamy, sizeof(double) * ny, cudaMemcpyDeviceToDevice));
-    for (int k = 0; k < 4; ++k) c->fdm_dir[k] = dirichlet_wesn[k];
-    c->fdm_nxg = (int)nxg;
-    c->fdm_block = (int)block;
-    c->fdm_ready = 1;
+    if (den_floor < 0) den_floor = fdm_den_floor(c->g);
+    const MeshDev& g = c->g;
+    if (!c->has_comm) return fdm_plan_build(c->plan[slot], g, x->lo, x->cnt, x->fold, x->Qe, x->Qo, x->lam, y->lo, y->cnt, y->fold,
+                                            y->Qe, y->Qo, y->lam, outside, 2, den_floor);
+    // partitioned: x is the GLOBAL pencil, unfolded; x->Qe = the slab's rows [NX][nmodes] of the global Q (zero rows at
+    // eliminated end nodes), x->lam[nmodes]; x->lo / x->cnt = the lines of the SLAB the operator acts on.
+    if (x->fold) { set_error("sem_ctx_set_fdm: the x direction of a partitioned mesh is not folded"); return -2; }
+    sem_ctx::FdmDist& d = c->dist[slot];
+    fdm_dist_free(d);
+    const int world = c->comm.world;
+    d.outside = outside;
+    d.den_floor = den_floor;
+    d.nmodes = x->nmodes;
+    d.B = round_up((d.nmodes + world - 1) / world, 128);
+    d.modesP = d.B * world;
+    d.s4 = x->lo;
+    d.m4 = x->cnt;
+    d.m4p = round_up(d.m4, 128);
+    d.s1 = std::max(x->lo, g.has_left ? 1 : 0);               // the interface line is summed from the left rank's copy
+    d.k1 = x->lo + x->cnt - d.s1;
+    d.k1p = round_up(d.k1, 16);
+    if (fdm_dir_build(d.y, y->lo, y->cnt, y->fold, y->Qe, y->Qo, y->lam)) return -1;
+    d.cols = std::max(round_up(y->cnt, 128), d.y.nep + d.y.nop);
+    auto zalloc = [](double** p, size_t n) -> int {
+        SEM_CUDA(cudaMalloc(p, sizeof(double) * n));
+        SEM_CUDA(cudaMemset(*p, 0, sizeof(double) * n));
+        return 0;
+    };
+    if (zalloc(&d.QxT, (size_t)d.modesP * d.k1p) || zalloc(&d.Qx, (size_t)d.m4p * d.modesP) || zalloc(&d.lamx, d.modesP) ||
+        zalloc(&d.R, (size_t)d.k1p * d.cols) || zalloc(&d.T, (size_t)d.modesP * d.cols) || zalloc(&d.mA, (size_t)d.B * d.cols) ||
+        zalloc(&d.mB, (size_t)d.B * d.cols) || zalloc(&d.X, (size_t)d.m4p * d.cols))
+        return -1;
+    const dim3 blk(128);
+    k_pad_rows<<<dim3((unsigned)((d.nmodes + 127) / 128), (unsigned)d.k1), blk>>>(x->Qe, d.nmodes, d.s1, d.k1, d.nmodes, d.QxT, d.k1p, 1);
+    k_pad_rows<<<dim3((unsigned)((d.nmodes + 127) / 128), (unsigned)d.m4), blk>>>(x->Qe, d.nmodes, d.s4, d.m4, d.nmodes, d.Qx, d.modesP, 0);
+    SEM_CUDA(cudaGetLastError());
+    SEM_CUDA(cudaMemcpy(d.lamx, x->lam, sizeof(double) * d.nmodes, cudaMemcpyDeviceToDevice));
+    SEM_CUDA(cudaDeviceSynchronize());
+    d.ready = 1;
     return 0;
 }
 
-// z = K_II^-1 r on the nodes that carry no Dirichlet row, z = r on the Dirichlet nodes.  r and z may not alias.
 // Partitioned mesh: the x transform couples all slabs, so it is distributed -- every rank forms its contribution
-// Qx_r^T R_r to all modes (one GEMM over its own lines; the duplicated interface line is taken from the left rank only), a
+// Qx_r^T R_r to all modes (one product over its own lines; the duplicated interface line is taken from the left rank only), a
 // reduce-scatter over NVLink leaves each rank with a block of modes, the y transforms and the spectral scaling are local to
-// that block, an all-gather returns all modes and one GEMM with the slab's rows of Qx gives the slab of the result.  The
+// that block, an all-gather returns all modes and one product with the slab's rows of Qx gives the slab of the result.  The
 // preconditioner is the exact inverse on any number of GPUs: the Krylov iteration count does not depend on the partition.
-static int fdm_apply(sem_ctx* c, const double* r, double* z, cudaStream_t st) {
-    if (!c->fdm_ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called"); return -2; }
-    const int nx = c->g.NX, ny = c->g.NY, ld = c->g.LD, nxg = c->fdm_nxg;
-    const double one = 1.0, zero = 0.0;
-    SEM_CUBLAS(cublasSetStream(c->blas, st));
-    // a row-major [NX][LD] vec is the column-major matrix R^T (ny x nx, leading dimension LD); a row-major Q is the
-    // column-major Q^T.  Steps: T1 = Qx^T R, Z = T1 Qy, Z /= (lx + ly), T2 = Z Qy^T, X = Qx T2 -- written for the transposes.
-    if (!c->has_comm) {
-        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nx, nx, &one, r, ld, c->fQx, nx, &zero, c->fT1, ld));
-        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT1, ld, &zero, c->fT2, ld));
-        if (aux_fdm_scale(c->g, c->fLx, c->fLy, c->fT2, nx, st)) return -1;
-        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, c->fT2, ld, &zero, c->fT1, ld));
-        SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nx, &one, c->fT1, ld, c->fQx, nx, &zero, z, ld));
-        return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
-    }
-    const int B = c->fdm_block, me = c->comm.rank;
-    const int skip = c->g.has_left ? 1 : 0;                    // the interface line is summed from the left rank's copy
-    double* mine1 = c->fT2;                                    // this rank's block of modes (B x LD), then Z
-    double* mine2 = c->fT2 + (size_t)B * ld;                   // T2 block
-    // contribution of this slab to all modes: T1p (nxg x ny) = Qx_r[skip:, :]^T R_r[skip:, :]
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nxg, nx - skip, &one, r + (size_t)skip * ld, ld,
-                           c->fQx + (size_t)skip * nxg, nxg, &zero, c->fT1, ld));
-    if (comm_reduce_scatter_sum(c->comm, c->fT1, mine1, (size_t)B * ld, st)) return -1;
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, B, ny, &one, c->fQy, ny, mine1, ld, &zero, mine2, ld));
-    if (aux_fdm_scale(c->g, c->fLx + (size_t)me * B, c->fLy, mine2, B, st)) return -1;
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, B, ny, &one, c->fQy, ny, mine2, ld, &zero, mine1, ld));
-    if (comm_allgather(c->comm, mine1, c->fT1, (size_t)B * ld, st)) return -1;
-    SEM_CUBLAS(cublasDgemm(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nxg, &one, c->fT1, ld, c->fQx, nxg, &zero, z, ld));
-    return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st);
+static int fdm_dist_apply(sem_ctx* c, sem_ctx::FdmDist& d, const double* r, double* z, cudaStream_t st) {
+    const MeshDev& g = c->g;
+    const int ycols = round_up(d.y.cnt, 128);
+    FdmDir x1, x4;
+    std::memset(&x1, 0, sizeof(x1));
+    x1.lo = d.s1; x1.cnt = d.k1; x1.ne = d.k1;
+    x4 = x1;
+    x4.lo = d.s4; x4.cnt = d.m4; x4.ne = d.m4;
+    if (fdm_fold_x(x1, d.y.lo, d.y.cnt, r, 0, g.LD, d.R, d.cols, 0, 1, st)) return -1;
+    GemmArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nprob = 1; a.batch = 1;
+    a.p[0] = GemmProblem{d.QxT, d.R, d.T, d.k1p, d.cols, d.cols, 0, 0, 0, d.modesP, ycols, d.k1p, nullptr, nullptr};
+    if (gemm_launch(a, EPI_NONE, st)) return -1;
+    if (comm_reduce_scatter_sum(c->comm, d.T, d.mA, (size_t)d.B * d.cols, st)) return -1;
+    if (fdm_fold_y(d.y, d.mA, d.mB, d.B, d.cols, 0, 1, st)) return -1;
+    if (fdm_step_y(d.y, false, d.mB, d.mA, d.B, d.cols, 0, d.lamx + (size_t)c->comm.rank * d.B, d.den_floor, 1, st)) return -1;
+    if (fdm_step_y(d.y, true, d.mA, d.mB, d.B, d.cols, 0, nullptr, 0.0, 1, st)) return -1;
+    if (fdm_unfold_y(d.y, d.mB, d.mA, d.B, d.cols, 0, 1, st)) return -1;
+    if (comm_allgather(c->comm, d.mA, d.T, (size_t)d.B * d.cols, st)) return -1;
+    a.p[0] = GemmProblem{d.Qx, d.T, d.X, d.modesP, d.cols, d.cols, 0, 0, 0, d.m4p, ycols, d.modesP, nullptr, nullptr};
+    if (gemm_launch(a, EPI_NONE, st)) return -1;
+    return fdm_unfold_x(x4, d.y.lo, d.y.cnt, d.X, d.cols, 0, r, z, 0, g, d.outside, 1, st);
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (not validated on a GPU in round 1, off unless sem_krylov.precond == 3): boundary block of the NS pressure
-// rows.  The pressure-Neumann rows K[mask,:] p (NS:119,157) are scaled by 1/M in the reference's Schur preconditioner, which
-// leaves eigenvalues ~ 2e4 and costs two thirds of the Krylov iterations (scratch/schur/p12.py).  Block
-// elimination instead:  z_I = mass sweep as before,  z_B = K_BB^-1 (r_B - K_BI z_I)  with the dense inverse of K restricted
-// to the boundary pressure nodes (a ring of 4(n-1) nodes; the pin node is excluded and keeps its identity row).  The member
-// of the singular system's solution set is unchanged: l_c vanishes on the boundary, so S~^T l_c = M_p l_c still holds.
-// idx_host[nb]: offsets ix*LD + iy of the boundary nodes;  inv_dev: DEVICE, row-major nb x nb.  One GPU only.
-// ---------------------------------------------------------------------------------------------------------------
-extern "C" int sem_ctx_set_pbb(sem_ctx* c, const long long* idx_host, int nb, const double* inv_dev) {
-    SEM_CHECK_CTX(c);
-    if (c->has_comm) { set_error("sem_ctx_set_pbb: not available on a partitioned context"); return -2; }
-    if (nb <= 0 || !idx_host || !inv_dev) { set_error("sem_ctx_set_pbb: bad arguments"); return -2; }
-    const long long vlen = (long long)c->g.NX * c->g.LD;
-    for (int a = 0; a < nb; ++a)
-        if (idx_host[a] < 0 || idx_host[a] >= vlen) { set_error("sem_ctx_set_pbb: node offset out of range"); return -2; }
-    if (c->pbb_idx) { cudaFree(c->pbb_idx); cudaFree(c->pbb_inv); cudaFree(c->pbb_rhs); cudaFree(c->pbb_z); c->pbb_idx = nullptr; }
-    c->pbb_n = 0;
-    SEM_CUDA(cudaMalloc(&c->pbb_idx, sizeof(long long) * nb));
-    SEM_CUDA(cudaMalloc(&c->pbb_inv, sizeof(double) * (size_t)nb * nb));
-    SEM_CUDA(cudaMalloc(&c->pbb_rhs, sizeof(double) * nb));
-    SEM_CUDA(cudaMalloc(&c->pbb_z, sizeof(double) * nb));
-    SEM_CUDA(cudaMemcpy(c->pbb_idx, idx_host, sizeof(long long) * nb, cudaMemcpyHostToDevice));
-    SEM_CUDA(cudaMemcpy(c->pbb_inv, inv_dev, sizeof(double) * (size_t)nb * nb, cudaMemcpyDeviceToDevice));
-    c->pbb_n = nb;
+// nf fields `stride` doubles apart; r and z may alias
+static int fdm_apply(sem_ctx* c, int slot, const double* r, double* z, int nf, long long stride, cudaStream_t st) {
+    if (!c->has_comm) {
+        if (!c->plan[slot].ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called for this slot"); return -2; }
+        return fdm_plan_apply(c->plan[slot], c->g, r, z, nf, stride, st);
+    }
+    if (!c->dist[slot].ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called for this slot"); return -2; }
+    for (int f = 0; f < nf; ++f)
+        if (fdm_dist_apply(c, c->dist[slot], r + f * stride, z + f * stride, st)) return -1;
     return 0;
 }
 
-// z_p (already holding the mass sweep) -> boundary entries replaced by K_BB^-1 (r_B - K_BI z_I); q: scratch vec
-static int pbb_apply(sem_ctx* c, const double* rc, double* zp, double* q, cudaStream_t st) {
-    const int nb = c->pbb_n;
-    if (nb <= 0) { set_error("pbb_apply: sem_ctx_set_pbb has not been called"); return -2; }
-    if (aux_pbb_zero(zp, c->pbb_idx, nb, st)) return -1;
-    // (K z)[boundary nodes] with z_B = 0 is K_BI z_I (the pin node, if it lies on the boundary, is skipped and keeps r_pin)
-    if (aux_neumann_rows(c->g, c->tab(), zp, q, c->pin_gx, c->pin_iy, 1, st)) return -1;
-    if (aux_pbb_gather(rc, q, c->pbb_idx, nb, c->pbb_rhs, st)) return -1;
-    const double one = 1.0, zero = 0.0;
-    SEM_CUBLAS(cublasSetStream(c->blas, st));
-    // row-major INV is the column-major INV^T: y = (INV^T)^T x
-    SEM_CUBLAS(cublasDgemv(c->blas, CUBLAS_OP_T, nb, nb, &one, c->pbb_inv, nb, c->pbb_rhs, 1, &zero, c->pbb_z, 1));
-    return aux_pbb_scatter(c->pbb_z, c->pbb_idx, nb, zp, st);
+extern "C" int sem_fdm_apply(sem_ctx* c, int slot, const double* r, double* z, int nf, void* stream) {
+    SEM_CHECK_CTX(c);
+    if (slot < 0 || slot >= SEM_FDM_SLOTS || nf < 1 || nf > 2) { set_error("sem_fdm_apply: bad slot / field count"); return -2; }
+    return fdm_apply(c, slot, r, z, nf, (long long)c->g.NX * c->g.LD, (cudaStream_t)stream);
 }
 
-// Two fields at once (the velocity components of the NS preconditioner, `stride` doubles apart): the same four GEMMs as
-// strided-batched calls, one scaling and one boundary launch -- 6 launches instead of 12.  On the reference's meshes
-// (65 x 65 nodes) every one of them is pure launch latency (4.3 us per GEMM, profiles/README.md).
-static int fdm_apply2(sem_ctx* c, const double* r, double* z, long long stride, cudaStream_t st) {
-    if (c->has_comm) return (fdm_apply(c, r, z, st) || fdm_apply(c, r + stride, z + stride, st)) ? -1 : 0;
-    if (!c->fdm_ready) { set_error("fdm_apply: sem_ctx_set_fdm has not been called"); return -2; }
-    const int nx = c->g.NX, ny = c->g.NY, ld = c->g.LD;
-    const long long fs = (long long)nx * ld;
-    if (!c->fB1) {
-        SEM_CUDA(cudaMalloc(&c->fB1, sizeof(double) * 2 * fs));
-        SEM_CUDA(cudaMalloc(&c->fB2, sizeof(double) * 2 * fs));
-        SEM_CUDA(cudaMemset(c->fB1, 0, sizeof(double) * 2 * fs));   // the GEMMs never touch the pad columns
-        SEM_CUDA(cudaMemset(c->fB2, 0, sizeof(double) * 2 * fs));
+// ---------------------------------------------------------------------------------------------------------------
+// Navier-Stokes preconditioner: block lower-triangular  [[P_a, 0], [C, S~]]^-1  for the 3-field Jacobian of NS:138-160.
+//   P_a  = Laplacian inverse per velocity component (fast diagonalisation; identity rows on the walls), or Jacobi
+//   C    = continuity rows,  S~ = approximation of the pressure Schur complement, by `level` (sem_krylov.precond):
+//     1, 2  z_p = y / M_p                        the reference's own diagonal-mass preconditioner (NS:208-212)
+//     3     + boundary ring by block elimination  z_B = K_BB^-1 (y_B - K_BI z_I), K_BB^-1 = fixed Chebyshev polynomial
+//     4     two-level:  z1 = Pi Shat^+ Pi^T y  (structured coarse operator on the near-null space of the equal-order Schur
+//           complement),  r1 = y - S_0 z1,  z2 = M^-1 F_p K_N^+ r1  (pressure convection-diffusion),
+//           both followed by the ring elimination; then the rank-one correction that keeps GMRES on the reference's member
+//           of the singular system's solution set.
+// Every stage is restated on the CPU by oracle/ns_precond.py (test infrastructure) and compared stage by stage in
+// tests/test_gpu_parity.py.
+// ---------------------------------------------------------------------------------------------------------------
+static int ensure_kdiag(sem_ctx* c, cudaStream_t st);
+
+enum { SW_Y = 0, SW_Z1, SW_R1, SW_G0, SW_G1, SW_V0, SW_V1, SW_NR, SW_RHO, SW_E };
+
+extern "C" int sem_ctx_set_ns_schur(sem_ctx* c, const sem_ns_schur_desc* d) {
+    SEM_CHECK_CTX(c);
+    if (!d) { set_error("sem_ctx_set_ns_schur: null descriptor"); return -2; }
+    if (d->cheb_steps < 1 || d->cheb_steps > 8) { set_error("sem_ctx_set_ns_schur: 1..8 Chebyshev steps"); return -2; }
+    sem_ctx::NsSchur& q = c->sch;
+    schur_free(q);
+    const MeshDev& g = c->g;
+    const int n1 = g.P + 1, nexg = (g.NXg - 1) / g.P, ney = g.ney;
+    const size_t vlen = (size_t)g.NX * g.LD;
+    // tables: wl[n1] wr[n1] | x: ta tinv tcp [nexg+1] each | y: ta tinv tcp [ney+1] each | lfx[NXg] | lfy[NY]
+    const size_t ntab = 2 * n1 + 3 * (nexg + 1) + 3 * (ney + 1) + g.NXg + g.NY;
+    std::vector<double> h(ntab);
+    size_t o = 0;
+    auto put = [&](const double* src, size_t n) { size_t at = o; std::memcpy(h.data() + o, src, sizeof(double) * n); o += n; return at; };
+    const size_t o_wl = put(d->wl, n1), o_wr = put(d->wr, n1);
+    const size_t o_xa = put(d->ta_x, nexg + 1), o_xi = put(d->tinv_x, nexg + 1), o_xc = put(d->tcp_x, nexg + 1);
+    const size_t o_ya = put(d->ta_y, ney + 1), o_yi = put(d->tinv_y, ney + 1), o_yc = put(d->tcp_y, ney + 1);
+    const size_t o_lx = put(d->lfx, g.NXg), o_ly = put(d->lfy, g.NY);
+    SEM_CUDA(cudaMalloc(&q.tables, sizeof(double) * ntab));
+    SEM_CUDA(cudaMemcpy(q.tables, h.data(), sizeof(double) * ntab, cudaMemcpyHostToDevice));
+    q.px = PwDir{g.NXg, q.tables + o_wl, q.tables + o_wr, q.tables + o_xa, q.tables + o_xi, q.tables + o_xc};
+    q.py = PwDir{g.NY, q.tables + o_wl, q.tables + o_wr, q.tables + o_ya, q.tables + o_yi, q.tables + o_yc};
+    auto zalloc = [](double** p, size_t n) -> int {
+        SEM_CUDA(cudaMalloc(p, sizeof(double) * n));
+        SEM_CUDA(cudaMemset(*p, 0, sizeof(double) * n));
+        return 0;
+    };
+    // G0|G1 and V0|V1 are pairs of adjacent vectors (two-field FDM applies)
+    if (zalloc(&q.w[SW_G0], 2 * vlen) || zalloc(&q.w[SW_V0], 2 * vlen)) return -1;
+    for (int k : {SW_Y, SW_Z1, SW_R1, SW_NR, SW_RHO, SW_E})
+        if (zalloc(&q.w[k], vlen)) return -1;
+    if (zalloc(&q.lc, vlen) || zalloc(&q.mc, vlen) || zalloc(&q.sums, 2)) return -1;
+    q.ldcy = round_up(ney + 1, 2);
+    if (zalloc(&q.cx, (size_t)(nexg + 1) * g.LD) || zalloc(&q.cy, (size_t)g.NX * q.ldcy)) return -1;
+    const Regions rg{c->pin_gx, c->pin_iy};
+    if (member_vectors(g, c->tab(), rg, q.tables + o_lx, q.tables + o_ly, q.lc, q.mc, 0)) return -1;
+    SEM_CUDA(cudaDeviceSynchronize());
+    q.singular = d->singular;
+    q.two_level = d->two_level;
+    q.inv_den = d->inv_den;
+    // Chebyshev iteration for the diagonally scaled ring block with spectrum in [lo, hi]
+    const double theta = 0.5 * (d->cheb_hi + d->cheb_lo), delta = 0.5 * (d->cheb_hi - d->cheb_lo);
+    const double sigma = theta / delta;
+    double rho = 1.0 / sigma;
+    q.cheb_steps = d->cheb_steps;
+    q.cheb_inv_theta = 1.0 / theta;
+    for (int k = 0; k < d->cheb_steps; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma - rho);
+        q.cheb_a[k] = rho_new * rho;
+        q.cheb_b[k] = 2.0 * rho_new / delta;
+        rho = rho_new;
     }
-    const double one = 1.0, zero = 0.0;
-    SEM_CUBLAS(cublasSetStream(c->blas, st));
-    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_N, CUBLAS_OP_T, ny, nx, nx, &one, r, ld, stride, c->fQx, nx, 0, &zero,
-                                         c->fB1, ld, fs, 2));
-    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, 0, c->fB1, ld, fs, &zero,
-                                         c->fB2, ld, fs, 2));
-    if (aux_fdm_scale(c->g, c->fLx, c->fLy, c->fB2, nx, st, 2, fs)) return -1;
-    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_T, CUBLAS_OP_N, ny, nx, ny, &one, c->fQy, ny, 0, c->fB2, ld, fs, &zero,
-                                         c->fB1, ld, fs, 2));
-    SEM_CUBLAS(cublasDgemmStridedBatched(c->blas, CUBLAS_OP_N, CUBLAS_OP_N, ny, nx, nx, &one, c->fB1, ld, fs, c->fQx, nx, 0, &zero,
-                                         z, ld, stride, 2));
-    return aux_fdm_boundary(c->g, c->fdm_dir, r, z, st, 2, stride);
+    // w[SW_G1], w[SW_V1]: second halves of the pairs (not separately owned)
+    q.w[SW_G1] = nullptr;
+    q.w[SW_V1] = nullptr;
+    q.ready = 1;
+    return 0;
+}
+
+struct SchurWork {
+    double *Y, *Z1, *R1, *G0, *G1, *V0, *V1, *NR, *RHO, *E;
+};
+static SchurWork schur_work(const sem_ctx* c) {
+    const sem_ctx::NsSchur& q = c->sch;
+    const size_t vlen = (size_t)c->g.NX * c->g.LD;
+    return SchurWork{q.w[SW_Y], q.w[SW_Z1], q.w[SW_R1], q.w[SW_G0], q.w[SW_G0] + vlen, q.w[SW_V0], q.w[SW_V0] + vlen,
+                     q.w[SW_NR], q.w[SW_RHO], q.w[SW_E]};
+}
+
+// rows K[ring,:] x of a vector, completed across partition interfaces (the interface lines are cleared first: the kernel
+// writes ring nodes only and the exchange adds whole lines)
+static int ring_rows(sem_ctx* c, const double* x, double* q, cudaStream_t st) {
+    const MeshDev& g = c->g;
+    if (c->has_comm) {
+        if (g.has_left) SEM_CUDA(cudaMemsetAsync(q, 0, sizeof(double) * g.LD, st));
+        if (g.has_right) SEM_CUDA(cudaMemsetAsync(q + (size_t)(g.NX - 1) * g.LD, 0, sizeof(double) * g.LD, st));
+    }
+    if (aux_neumann_rows(g, c->tab(), x, q, c->pin_gx, c->pin_iy, 1, st)) return -1;
+    return exchange(c, {q}, st);
+}
+
+// z (given on the inner nodes and the pin, zero on the ring)  ->  z_B = K_BB^-1 (y_B - K_BI z_I) on the ring
+static int schur_add_ring(sem_ctx* c, double* z, const double* y, cudaStream_t st) {
+    sem_ctx::NsSchur& q = c->sch;
+    const SchurWork W = schur_work(c);
+    const Regions rg{c->pin_gx, c->pin_iy};
+    if (ring_rows(c, z, W.NR, st)) return -1;
+    if (ring_init(c->g, rg, y, W.NR, c->dKdiag, q.cheb_inv_theta, W.RHO, W.E, st)) return -1;
+    for (int k = 0; k < q.cheb_steps; ++k) {
+        if (ring_rows(c, W.E, W.NR, st)) return -1;
+        if (ring_step(c->g, rg, W.NR, c->dKdiag, q.cheb_a[k], q.cheb_b[k], z, W.RHO, W.E, st)) return -1;
+    }
+    return 0;
+}
+
+// out = v - Q v Q^T restricted to the interior grid, Q = I - P_W (transposed: Q^T):  the separable projector Pi (Pi^T).
+// u: work vector.  v and out may alias.
+static int schur_project(sem_ctx* c, int transposed, const double* v, double* u, double* out, cudaStream_t st) {
+    sem_ctx::NsSchur& q = c->sch;
+    const MeshDev& g = c->g;
+    if (pw_restrict(g, c->tab(), q.px, 0, transposed, v, q.cx, g.LD, st)) return -1;
+    if (c->has_comm && comm_allreduce_sum(c->comm, q.cx, ((g.NXg - 1) / g.P + 1) * g.LD, st)) return -1;
+    if (pw_solve(g, q.px, 0, q.cx, g.LD, st)) return -1;
+    if (pw_prolong(g, c->tab(), q.px, 0, transposed, q.cx, g.LD, v, u, st)) return -1;          // u = (I - P_x) v
+    if (pw_restrict(g, c->tab(), q.py, 1, transposed, u, q.cy, q.ldcy, st)) return -1;
+    if (pw_solve(g, q.py, 1, q.cy, q.ldcy, st)) return -1;
+    if (pw_prolong(g, c->tab(), q.py, 1, transposed, q.cy, q.ldcy, u, u, st)) return -1;        // u = (I - P_y) u
+    return aux_sub(v, u, out, (long long)g.NX * g.LD, st);                                      // out = v - u
+}
+
+// z1 = Pi Shat^+ Pi^T y on the inner nodes, z1[pin] = y[pin], zero on the ring
+static int schur_coarse(sem_ctx* c, const double* y, double* z1, cudaStream_t st) {
+    const SchurWork W = schur_work(c);
+    const Regions rg{c->pin_gx, c->pin_iy};
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    if (schur_inner(c->g, c->tab(), rg, y, nullptr, 0, W.G0, st)) return -1;
+    if (schur_project(c, 1, W.G0, W.G1, W.V0, st)) return -1;
+    if (fdm_apply(c, SEM_FDM_COARSE, W.V0, W.V1, 1, vlen, st)) return -1;
+    if (schur_project(c, 0, W.V1, W.G1, W.G0, st)) return -1;
+    return schur_inner(c->g, c->tab(), rg, W.G0, y, 0, z1, st);
+}
+
+// r1 = y - S_0 z1,  S_0 = D - C A_0^-1 G with the Stokes velocity block A_0 (what the fast diagonalisation inverts exactly)
+static int schur_stokes_res(sem_ctx* c, const double* y, const double* z1, double* tmp, double* r1, cudaStream_t st) {
+    const SchurWork W = schur_work(c);
+    const Regions rg{c->pin_gx, c->pin_iy};
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    MarchArgs A = zero_args();
+    A.a = z1; A.y0 = W.G0; A.y1 = W.G1; A.cconv = 1.0;
+    if (apply_and_exchange(c, MODE_G, A, {W.G0, W.G1}, st)) return -1;
+    if (schur_zero_boundary2(c->g, W.G0, W.G1, st)) return -1;
+    if (fdm_apply(c, SEM_FDM_MAIN, W.G0, W.V0, 2, vlen, st)) return -1;
+    MarchArgs B = zero_args();
+    B.a = W.V0; B.b = W.V1; B.y0 = tmp;
+    if (apply_and_exchange(c, MODE_DIV, B, {tmp}, st)) return -1;
+    if (ring_rows(c, z1, W.NR, st)) return -1;
+    return schur_stokes_residual(c->g, rg, y, W.NR, tmp, z1, r1, st);
+}
+
+// z2 = M^-1 F_p K_N^+ r1 on the inner nodes (F_p = K + Re (diag(u) G_x + diag(v) G_y) on the pressure nodes, K_N^+ = the
+// pseudo-inverse of the all-Neumann Laplacian by fast diagonalisation), z2[pin] = r1[pin], zero on the ring
+static int schur_pcd(sem_ctx* c, const sem_ns_state& lin, const double* r1, double* z2, cudaStream_t st) {
+    const SchurWork W = schur_work(c);
+    const Regions rg{c->pin_gx, c->pin_iy};
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    if (schur_inner(c->g, c->tab(), rg, r1, nullptr, 0, W.G0, st)) return -1;
+    if (fdm_apply(c, SEM_FDM_NEUMANN, W.G0, W.G1, 1, vlen, st)) return -1;
+    MarchArgs A = zero_args();
+    A.a = W.G1; A.U = lin.u; A.V = lin.v; A.cconv = lin.Re; A.y0 = W.V0;
+    if (apply_and_exchange(c, MODE_CD, A, {W.V0}, st)) return -1;
+    return schur_inner(c->g, c->tab(), rg, W.V0, r1, 1, z2, st);
+}
+
+// z = P^-1 r for r = (r_u | r_v | r_c), three vecs `vlen` apart; tmp: one scratch vec
+static int ns_precond_apply(sem_ctx* c, const sem_ns_state& lin, int level, const double* r, double* z, double* tmp,
+                            cudaStream_t st) {
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    if (level == 0) return aux_axpby(1.0, r, 0.0, z, 3 * vlen, st);
+    if (level >= 2) {
+        if (fdm_apply(c, SEM_FDM_MAIN, r, z, 2, vlen, st)) return -1;
+    } else if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) {
+        return -1;
+    }
+    MarchArgs A = zero_args();
+    A.a = z; A.b = z + vlen; A.y0 = tmp;
+    if (apply_and_exchange(c, MODE_DIV, A, {tmp}, st)) return -1;
+    const double* rc = r + 2 * vlen;
+    double* zp = z + 2 * vlen;
+    if (level <= 2) return aux_ns_schur_mass(c->g, c->tab(), rc, tmp, zp, c->pin_gx, c->pin_iy, st);
+    sem_ctx::NsSchur& q = c->sch;
+    if (!q.ready) { set_error("ns_precond_apply: sem_ctx_set_ns_schur has not been called"); return -2; }
+    const SchurWork W = schur_work(c);
+    const Regions rg{c->pin_gx, c->pin_iy};
+    if (schur_rhs(c->g, rg, rc, tmp, W.Y, st)) return -1;
+    if (level == 3 || !q.two_level) {
+        if (schur_inner(c->g, c->tab(), rg, W.Y, W.Y, 1, zp, st)) return -1;
+        return schur_add_ring(c, zp, W.Y, st);
+    }
+    if (schur_coarse(c, W.Y, W.Z1, st)) return -1;
+    if (schur_add_ring(c, W.Z1, W.Y, st)) return -1;
+    if (schur_stokes_res(c, W.Y, W.Z1, tmp, W.R1, st)) return -1;
+    if (schur_pcd(c, lin, W.R1, zp, st)) return -1;
+    if (schur_add_ring(c, zp, W.R1, st)) return -1;
+    if (aux_axpby(1.0, W.Z1, 1.0, zp, vlen, st)) return -1;
+    if (q.singular) {
+        if (ctx_multi_dot(c, q.mc, vlen, 1, zp, q.sums, 1, vlen, st)) return -1;
+        if (ctx_multi_dot(c, q.lc, vlen, 1, W.Y, q.sums + 1, 1, vlen, st)) return -1;
+        if (member_update(c->g, q.lc, q.sums, q.inv_den, zp, st)) return -1;
+    }
+    return 0;
+}
+
+// One application of the preconditioner / of one of its stages (tests compare them with oracle/ns_precond.py).
+//   what 0: z3 = P^-1 r3 at `level`            (in = 3 vecs, out = 3 vecs)
+//        1: out = coarse(in)   2: out = in2 with the ring added for right-hand side in (add_ring)
+//        3: out = in - S_0 in2  (r1 for y = in, z1 = in2)   4: out = pcd(in)      (single vecs)
+extern "C" int sem_ns_precond_debug(sem_ctx* c, const sem_ns_state* s, int what, int level, const double* in, const double* in2,
+                                    double* out, void* stream) {
+    SEM_CHECK_CTX(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long vlen = (long long)c->g.NX * c->g.LD;
+    if (ensure_kdiag(c, st)) return -1;
+    double* tmp = nullptr;
+    SEM_CUDA(cudaMalloc(&tmp, sizeof(double) * vlen));
+    SEM_CUDA(cudaMemsetAsync(tmp, 0, sizeof(double) * vlen, st));
+    int rc = 0;
+    if (what != 0 && !c->sch.ready) { set_error("sem_ns_precond_debug: sem_ctx_set_ns_schur has not been called"); rc = -2; }
+    else if (what == 0) rc = ns_precond_apply(c, *s, level, in, out, tmp, st);
+    else if (what == 1) rc = schur_coarse(c, in, out, st);
+    else if (what == 2) { rc = aux_axpby(1.0, in2, 0.0, out, vlen, st); if (!rc) rc = schur_add_ring(c, out, in, st); }
+    else if (what == 3) rc = schur_stokes_res(c, in, in2, tmp, out, st);
+    else if (what == 4) rc = schur_pcd(c, *s, in, out, st);
+    else { set_error("sem_ns_precond_debug: unknown stage"); rc = -2; }
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -900,7 +1129,10 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
     };
     while (true) {
         kr->resnorm = beta;
-        if (!(beta > kr->atol)) return 0;
+        // a NaN / Inf residual (non-finite input, overflowing operator, broken-down singular system) is a failure, not
+        // convergence: the reference's lgmres reports info != 0 and the solvers raise (CD:149-150, NS:225-226)
+        if (!std::isfinite(beta)) { set_error("gmres: non-finite residual"); return -3; }
+        if (beta <= kr->atol) return 0;
         if (kr->iters >= kr->max_iters) return kr->iters > 0 ? kr->iters : 1;
         if (aux_axpby(1.0 / beta, V, 0.0, w, n, st)) return -1;
         if (aux_axpby(1.0, w, 0.0, V, n, st)) return -1;
@@ -968,7 +1200,9 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
         kr->iters += done;   // Arnoldi steps that enter the solution
         const int j = done;
         // y = H^-1 g (back substitution on the rotated upper-triangular H), x += Pinv(V y)
-        const int k = j;
+        int k = j;
+        for (int i = 0; i < k; ++i)   // a zero pivot (exact breakdown of a singular system): use the columns before it
+            if (!(std::fabs(H[(size_t)i * (m + 1) + i]) > 0.0)) { k = i; break; }
         for (int i = k - 1; i >= 0; --i) {
             double s = gv[i];
             for (int q = i + 1; q < k; ++q) s -= H[(size_t)q * (m + 1) + i] * yv[q];
@@ -1035,7 +1269,7 @@ extern "C" int sem_cd_solve(sem_ctx* c, const sem_cd_state* s, const double* rhs
     vecop Aop = [&](const double* xx, double* yy) { return sem_cd_jvp(c, &lin, xx, nullptr, nullptr, yy, (void*)st); };
     vecop Pinv = [&](const double* r, double* z) {
         if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, vlen, st);
-        if (kr->precond == 2) return fdm_apply(c, r, z, st);
+        if (kr->precond == 2) return fdm_apply(c, SEM_FDM_MAIN, r, z, 1, vlen, st);
         return aux_cd_jacobi(c->g, bc, c->dKdiag, r, z, st);
     };
     GmresLayout L{vlen, 1, vlen};
@@ -1074,20 +1308,7 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
     // C = continuity rows, M_p = diagonal mass with the pin row passed through (the reference's Schur preconditioner,
     // NS:208-212).  With this structure GMRES converges to the same member of the (singular, consistent) system's
     // solution family as the reference's Schur-complement iteration -- see DESIGN.md.
-    vecop Pinv = [&](const double* r, double* z) {
-        if (kr->precond == 0) return aux_axpby(1.0, r, 0.0, z, n, st);
-        if (kr->precond == 2 || kr->precond == 3) {
-            if (fdm_apply2(c, r, z, vlen, st)) return -1;
-        } else if (aux_ns_jacobi(c->g, c->dKdiag, lin.gxu, lin.gyv, r, r + vlen, z, z + vlen, st)) {
-            return -1;
-        }
-        MarchArgs A = zero_args();
-        A.a = z; A.b = z + vlen; A.y0 = tmp;
-        if (apply_and_exchange(c, MODE_DIV, A, {tmp}, st)) return -1;
-        if (aux_ns_schur_mass(c->g, c->tab(), r + 2 * vlen, tmp, z + 2 * vlen, c->pin_gx, c->pin_iy, st)) return -1;
-        if (kr->precond == 3) return pbb_apply(c, r + 2 * vlen, z + 2 * vlen, tmp, st);   // experimental, see sem_ctx_set_pbb
-        return 0;
-    };
+    vecop Pinv = [&](const double* r, double* z) { return ns_precond_apply(c, lin, kr->precond, r, z, tmp, st); };
     GmresLayout L{n, 3, vlen};
     const int rc = gmres(c, L, Aop, Pinv, rhs3, x3, kr, V, w, t, vin, st, use_graph);
     SEM_CUDA(cudaStreamSynchronize(st));

@@ -83,7 +83,8 @@ class SemDevice:
         self.N_local = self.NX * self.NY
         self._pinned = {}
         self.has_fdm = False
-        self.has_pbb = False
+        self.has_ns_schur = False
+        self.ns_singular = False
         if self.part is not None and self.part.world > 1:
             self._attach_comm()
 
@@ -165,61 +166,177 @@ class SemDevice:
         Iy = torch.from_numpy(SEM.interp_matrix_1d(self.P, self.N_ey, self.dy, ys)).to(self.tdev)
         return ((Ix @ vec[:, :self.NY]) @ Iy.T).cpu().numpy()
 
-    # ---- fast-diagonalisation preconditioner ---------------------------------------------------------------------------
-    def _fdm_1d(self, nel, h, dir_lo, dir_hi):
-        """Generalised eigenpairs of the assembled 1-D pencil (K1, M1) of ``nel`` elements of size ``h`` (SEM.py:186-203
-        restricted to one direction) with the Dirichlet end nodes eliminated.  Returns (Q [n, n] row-major with zero
-        rows at eliminated nodes and zero unused columns, lam [n]) on the device: Q^T M1 Q = I, Q^T K1 Q = diag(lam)."""
+    # ---- fast-diagonalisation plans (sem_ctx_set_fdm) ----------------------------------------------------------------------
+    _EIG_HOST_MAX = 2100     # pencils up to this size are diagonalised on the host (LAPACK), larger ones with torch on the GPU
+
+    def _pencil_1d(self, nel, h):
+        """Dense assembled 1-D stiffness matrix, mass vector and weak-gradient matrix of ``nel`` elements of size ``h``
+        (the x or y factor of the Kronecker-structured global matrices, SEM.py:170-223), as float64 torch tensors on the
+        host (small) or on the device (large)."""
         P, n = self.P, nel * self.P + 1
-        Ks = torch.from_numpy(self._Ks).to(self.tdev) * (2.0 / h)
-        w = torch.from_numpy(self._w).to(self.tdev) * (0.5 * h)
-        rows = (torch.arange(nel, device=self.tdev)[:, None] * P + torch.arange(P + 1, device=self.tdev)[None, :])
-        K = torch.zeros((n, n), dtype=torch.float64, device=self.tdev)
+        dev = torch.device("cpu") if n <= self._EIG_HOST_MAX else self.tdev
+        Ks = torch.from_numpy(self._Ks).to(dev) * (2.0 / h)
+        Gs = torch.from_numpy(self._w[:, None] * self._D).to(dev)                  # G_s = diag(w) D, GLL.py:62-70
+        w = torch.from_numpy(self._w).to(dev) * (0.5 * h)
+        rows = (torch.arange(nel, device=dev)[:, None] * P + torch.arange(P + 1, device=dev)[None, :])
         flat = (rows[:, :, None] * n + rows[:, None, :]).reshape(-1)
+        K = torch.zeros((n, n), dtype=torch.float64, device=dev)
         K.view(-1).index_add_(0, flat, Ks.expand(nel, P + 1, P + 1).reshape(-1))
-        M = torch.zeros(n, dtype=torch.float64, device=self.tdev)
+        G = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        G.view(-1).index_add_(0, flat, Gs.expand(nel, P + 1, P + 1).reshape(-1))
+        M = torch.zeros(n, dtype=torch.float64, device=dev)
         M.index_add_(0, rows.reshape(-1), w.expand(nel, P + 1).reshape(-1))
-        lo, hi = (1 if dir_lo else 0), (n - 1 if dir_hi else n)
-        s = 1.0 / torch.sqrt(M[lo:hi])
-        A = K[lo:hi, lo:hi] * s[:, None] * s[None, :]
-        lam, V = torch.linalg.eigh(0.5 * (A + A.T))
-        Q = torch.zeros((n, n), dtype=torch.float64, device=self.tdev)
-        Q[lo:hi, :hi - lo] = V * s[:, None]
-        lam_full = torch.ones(n, dtype=torch.float64, device=self.tdev)
-        lam_full[:hi - lo] = lam.clamp_min(0.0)
-        return Q.contiguous(), lam_full
+        return K, M, G
+
+    @staticmethod
+    def _eigh_scaled(A, m):
+        """Generalised eigenpairs of (A, diag(m)): returns (lam, C) with C^T diag(m) C = I; tiny |lam| clamped to 0."""
+        s = 1.0 / torch.sqrt(m)
+        B = A * s[:, None] * s[None, :]
+        lam, V = torch.linalg.eigh(0.5 * (B + B.T))
+        lam = torch.where(lam.abs() < 1e-11 * lam.abs().max(), torch.zeros_like(lam), lam)
+        return lam, V * s[:, None]
+
+    def _fdm_dir(self, A, M, lo, hi, fold, keep):
+        """One direction of a plan: eigenpairs of the pencil (A[lo:hi, lo:hi], diag(M[lo:hi])).  fold: parity-split (the pencil
+        must be symmetric about the centre).  Returns a ``sem_fdm_dir`` whose device arrays are appended to ``keep``."""
+        cnt = hi - lo
+        Aa, Ma = A[lo:hi, lo:hi], M[lo:hi]
+        if fold:
+            h, ne = cnt // 2, (cnt + 1) // 2
+            Fe = torch.zeros((cnt, ne), dtype=torch.float64, device=A.device)
+            idx = torch.arange(h, device=A.device)
+            Fe[idx, idx] = 1.0
+            Fe[cnt - 1 - idx, idx] = 1.0
+            if cnt % 2:
+                Fe[h, h] = 1.0
+            Fo = torch.zeros((cnt, h), dtype=torch.float64, device=A.device)
+            Fo[idx, idx] = 1.0
+            Fo[cnt - 1 - idx, idx] = -1.0
+            le, Ce = self._eigh_scaled(Fe.T @ Aa @ Fe, Fe.T @ Ma)
+            if h:
+                lo_, Co = self._eigh_scaled(Fo.T @ Aa @ Fo, Fo.abs().T @ Ma)
+            else:
+                lo_, Co = le[:0], Ce[:0, :0]
+            lam = torch.cat([le, lo_])
+        else:
+            lam, Ce = self._eigh_scaled(Aa, Ma)
+            Co = Ce[:0, :0]
+        Qe, Qo, lam = (t.to(self.tdev).contiguous() for t in (Ce, Co, lam))
+        keep += [Qe, Qo, lam]
+        return L.sem_fdm_dir(int(lo), int(cnt), int(bool(fold)), Qe.data_ptr(), Qo.data_ptr() if Qo.numel() else None,
+                             lam.data_ptr(), int(cnt))
+
+    def _fdm_dir_global(self, A, M, lo, hi, keep):
+        """Unfolded x direction of a PARTITIONED plan: the slab's rows of the global eigenvector matrix."""
+        part = self.part
+        lam, C = self._eigh_scaled(A[lo:hi, lo:hi], M[lo:hi])
+        n = A.shape[0]
+        Q = torch.zeros((n, hi - lo), dtype=torch.float64, device=A.device)
+        Q[lo:hi] = C
+        Qs = Q[part.line_begin:part.line_end + 1].to(self.tdev).contiguous()
+        lam = lam.to(self.tdev).contiguous()
+        keep += [Qs, lam]
+        l0 = max(lo, part.line_begin) - part.line_begin
+        l1 = min(hi, part.line_end + 1) - part.line_begin
+        return L.sem_fdm_dir(int(l0), int(l1 - l0), 0, Qs.data_ptr(), None, lam.data_ptr(), int(hi - lo))
+
+    def _set_plan(self, slot, Ax, Mx, xr, Ay, My, yr, outside):
+        keep = []
+        partitioned = self.part is not None and self.part.world > 1
+        if partitioned:
+            dx_ = self._fdm_dir_global(Ax, Mx, xr[0], xr[1], keep)
+        else:
+            dx_ = self._fdm_dir(Ax, Mx, xr[0], xr[1], xr[0] + xr[1] == Ax.shape[0], keep)
+        dy_ = self._fdm_dir(Ay, My, yr[0], yr[1], yr[0] + yr[1] == Ay.shape[0], keep)
+        torch.cuda.current_stream(self.tdev).synchronize()
+        L.check(self.lib.sem_ctx_set_fdm(self.ctx, int(slot), C.byref(dx_), C.byref(dy_), int(outside), 0.0), "sem_ctx_set_fdm")
 
     def setup_fdm(self, dirichlet_wesn):
-        """Build and hand over the fast-diagonalisation preconditioner for the given Dirichlet sides (W, E, S, N).  On a
-        partitioned mesh the x transform is distributed (GEMM + reduce-scatter, all-gather + GEMM): still the exact inverse."""
+        """Fast-diagonalisation plan of the Laplacian with the given Dirichlet sides (W, E, S, N) -- slot 0: the preconditioner
+        of the CD solve and the velocity block of the NS preconditioner.  Identity rows (z = r) on the Dirichlet nodes."""
         dW, dE, dS, dN = (bool(v) for v in dirichlet_wesn)
-        Qx, lx = self._fdm_1d(self.N_ex, self.dx, dW, dE)        # the GLOBAL x pencil (every rank solves the same small problem)
-        if self.part is not None and self.part.world > 1:
-            # exact distributed FDM: this rank keeps the rows of Qx that belong to its slab (all modes)
-            Qx = Qx[self.part.line_begin:self.part.line_end + 1].contiguous()
-        Qy, ly = self._fdm_1d(self.N_ey, self.dy, dS, dN)
-        flags = (C.c_int * 4)(int(dW), int(dE), int(dS), int(dN))
-        torch.cuda.current_stream(self.tdev).synchronize()
-        L.check(self.lib.sem_ctx_set_fdm(self.ctx, Qx.data_ptr(), lx.data_ptr(), Qy.data_ptr(), ly.data_ptr(), flags),
-                "sem_ctx_set_fdm")
+        Kx, Mx, _ = self._pencil_1d(self.N_ex, self.dx)
+        Ky, My, _ = self._pencil_1d(self.N_ey, self.dy)
+        nx, ny = Kx.shape[0], Ky.shape[0]
+        self._set_plan(0, Kx, Mx, (int(dW), nx - int(dE)), Ky, My, (int(dS), ny - int(dN)), 1)
         self.has_fdm = True
 
-    def setup_pressure_boundary_block(self, pin):
-        """EXPERIMENTAL (not validated on a GPU in round 1; used only by ``NavierStokesSolver(precond='fdm+bb')``): dense
-        inverse of the stiffness matrix restricted to the boundary pressure nodes, for the block elimination of the
-        pressure-Neumann rows in the NS preconditioner.  Whole mesh on one GPU, at most 8192 boundary
-        nodes (a banded ring solve is the production answer)."""
+    def setup_ns_schur(self, pin):
+        """Everything the Schur-complement stages of the NS preconditioner need (sem_krylov.precond 3 / 4, DESIGN.md section 4;
+        CPU mirror: oracle/ns_precond.py): the all-Neumann pressure Laplacian (slot 1), the structured coarse operator
+        Shat = R(sigma) (x) M + M (x) R(sigma) on the interior pressure nodes (slot 2), the tables of the separable coarse-space
+        projector, the 1-D factors of the Jacobian's left null vector and the Chebyshev parameters of the ring block."""
+        from numpy.polynomial import legendre as npl
+        P = self.P
+        xi = GLL.standard_nodes(P)[0]
+        LP = npl.legval(xi, [0] * P + [1])
+        xn = 0.5 * (xi + 1.0)
+        wl = np.ascontiguousarray((1.0 - xn) * LP)
+        wr = np.ascontiguousarray(xn * LP)
+        two_level = P >= 2
+        dirs = []
+        for nel, h in ((self.N_ex, self.dx), (self.N_ey, self.dy)):
+            K, M, G = self._pencil_1d(nel, h)
+            n = K.shape[0]
+            sign = np.array([(-1.0) ** m if P % 2 else 1.0 for m in range(nel)])
+            s = np.zeros(n)
+            lf = np.zeros(n)
+            for m in range(nel):
+                s[m * P:m * P + P + 1] = sign[m] * LP
+                lf[m * P:m * P + P + 1] = 1.0 + sign[m] * LP if P % 2 else 1.0 - LP
+            Mh = M.cpu().numpy()
+            # tridiagonal Gram matrix T = W_I^T M_II W_I of the coarse-space functions (hat_k * s), interior nodes only
+            W = np.zeros((n, nel + 1))
+            for m in range(nel):
+                W[m * P:m * P + P + 1, m] = np.maximum(W[m * P:m * P + P + 1, m], 1.0 - xn)
+                W[m * P:m * P + P + 1, m + 1] = np.maximum(W[m * P:m * P + P + 1, m + 1], xn)
+            W *= s[:, None]
+            W[0] = 0.0
+            W[-1] = 0.0
+            T = W.T @ (Mh[:, None] * W)
+            b, a = np.diag(T).copy(), np.append(0.0, np.diag(T, -1))
+            csup = np.append(np.diag(T, 1), 0.0)
+            tinv, tcp = np.zeros(nel + 1), np.zeros(nel + 1)
+            prev = 0.0
+            for k in range(nel + 1):
+                den = b[k] - a[k] * prev
+                tinv[k] = 1.0 / den if den != 0.0 else 0.0
+                prev = csup[k] * tinv[k]
+                tcp[k] = prev
+            if two_level:
+                # coarse pencil (E^T R(sigma) E, M_II), R(sigma) = G E (K_II + sigma M_II)^-1 E^T G^T, sigma = lambda_s / 4
+                st = torch.from_numpy(s).to(K.device)
+                lam_s = float((st @ (K @ st)) / (st @ (M * st)))
+                X = torch.linalg.solve(K[1:-1, 1:-1] + 0.25 * lam_s * torch.diag(M[1:-1]), G[:, 1:-1].T)
+                R = G[:, 1:-1] @ X
+                R = 0.5 * (R + R.T)
+            else:
+                R = K
+            dirs.append(dict(K=K, M=M, R=R, n=n, lf=lf, a=a, tinv=tinv, tcp=tcp, Mh=Mh))
+        X_, Y_ = dirs
+        self._set_plan(1, X_["K"], X_["M"], (0, X_["n"]), Y_["K"], Y_["M"], (0, Y_["n"]), 0)
+        if two_level:
+            self._set_plan(2, X_["R"], X_["M"], (1, X_["n"] - 1), Y_["R"], Y_["M"], (1, Y_["n"] - 1), 0)
+        NYn = Y_["n"]
+        pin_ix, pin_iy = divmod(int(pin), NYn)
+        lcx, lcy = X_["lf"], Y_["lf"]
+        on_boundary = max(abs(lcx[0]), abs(lcx[-1]), abs(lcy[0]), abs(lcy[-1]))
+        singular = bool(on_boundary < 1e-12 and abs(lcx[pin_ix] * lcy[pin_iy]) < 1e-12)
+        den = float((X_["Mh"] * lcx * lcx).sum() * (Y_["Mh"] * lcy * lcy).sum())
+        arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in
+                (wl, wr, X_["a"], X_["tinv"], X_["tcp"], Y_["a"], Y_["tinv"], Y_["tcp"], lcx, lcy)]
         from . import SEM
-        if self.part is not None and self.part.world > 1:
-            raise L.SemError("the pressure boundary block needs the whole mesh on one GPU")
-        ix, iy, KBB = SEM.pressure_boundary_block(self.P, self.N_ex, self.N_ey, self.dx, self.dy, pin)
-        if ix.size > 8192:
-            raise L.SemError(f"pressure boundary block: {ix.size} boundary nodes exceed the dense limit of 8192")
-        inv = torch.linalg.inv(torch.from_numpy(KBB).to(self.tdev)).contiguous()
-        idx = np.ascontiguousarray(ix.astype(np.int64) * self.LD + iy.astype(np.int64))
-        torch.cuda.current_stream(self.tdev).synchronize()
-        L.check(self.lib.sem_ctx_set_pbb(self.ctx, idx.ctypes.data, int(idx.size), inv.data_ptr()), "sem_ctx_set_pbb")
-        self.has_pbb = True
+        cheb_lo, cheb_hi, cheb_steps = SEM.ring_chebyshev_parameters(P, self.N_ex, self.N_ey, self.dx, self.dy, int(pin))
+        desc = L.sem_ns_schur_desc(*[v.ctypes.data for v in arrs], int(singular), int(two_level),
+                                   1.0 / den if den > 0 else 0.0, cheb_lo, cheb_hi, cheb_steps)
+        L.check(self.lib.sem_ctx_set_ns_schur(self.ctx, C.byref(desc)), "sem_ctx_set_ns_schur")
+        self.has_ns_schur = True
+        self.ns_singular = singular
+
+    def fdm_apply(self, slot, r, z, nf=1):
+        L.check(self.lib.sem_fdm_apply(self.ctx, int(slot), r.data_ptr(), z.data_ptr(), int(nf), self.stream), "sem_fdm_apply")
+        return z
 
     # ---- single operators ------------------------------------------------------------------------------------------
     def apply_stiffness(self, x, y):
