@@ -63,6 +63,8 @@ class NavierStokesSolver:
             precond = 'full'
         self._precond = {'jacobi': 1, 'fdm': 2, 'fdm+bb': 3, 'full': 4}[precond]
         self._work = None
+        self._null = None            # left null vector of the Jacobian (coupled drivers: _get_update_inexact)
+        self._null_ready = False
         self.last_iters = 0
         self.last_resnorm = float('nan')
         self.krylov_iters = []       # iterations of every linear solve since construction
@@ -236,33 +238,37 @@ class NavierStokesSolver:
         self._solve_dev(self._out, self._x)
         return tuple(d.to_host(self._x[k]) for k in range(3))
 
-    def _get_update_inexact(self, dres_u, dres_v, dres_cont, rtol=1e-10, chunk=100, max_chunks=60):
+    def _get_update_inexact(self, dres_u, dres_v, dres_cont, rtol=1e-10):
         """``_get_update`` for right-hand sides that need not lie in the range of the (singular) Jacobian --
-        the block-Jacobi preconditioner of a coupled Newton-Krylov driver hands over arbitrary Krylov vectors.  GMRES runs
-        in warm-started chunks and stops at the tolerance ``max(mtol sqrt(N), rtol |rhs|)`` or as soon as a chunk no longer
-        reduces the residual by 5 % (it has reached the part of the right-hand side outside the range: the least-squares
-        solution); it never raises.  Not part of the reference API."""
+        the block-Jacobi preconditioner of a coupled Newton-Krylov driver hands over arbitrary Krylov vectors.  The right-hand
+        side is first projected onto the range, b <- b - l (l.b) / (l.l) with the analytic left null vector
+        (``SemDevice.ns_left_null_vector``), which makes the system consistent; the Krylov solver then converges to the same
+        member of the solution set as for a Newton step (tolerance ``max(mtol sqrt(N), rtol |rhs|)``).  Not part of the
+        reference API."""
         if not (self._have_sys and self._have_jac):
             raise RuntimeError('NavierStokes: _get_residuals and _calc_jacobians must precede a linear solve')
         d = self._dev
         for k, a in enumerate((dres_u, dres_v, dres_cont)):
             d.to_device(a, self._out[k])
         self._x.zero_()
+        kr = self._krylov()
+        if not d.has_ns_schur:
+            d.setup_ns_schur(int(self.N / 2))
+        if not self._null_ready:
+            self._null = d.ns_left_null_vector()
+            self._null_nrm2 = d.dot(self._null, self._null) if self._null is not None else 0.0
+            self._null_ready = True
+        if self._null is not None:
+            d.axpby(-d.dot(self._null, self._out) / self._null_nrm2, self._null, 1.0, self._out)
         rhs_norm = float(np.sqrt(d.dot(self._out, self._out)))
-        prev = rhs_norm
-        for _ in range(max_chunks):
-            kr = self._krylov()
-            kr.atol = max(kr.atol, rtol * rhs_norm)
-            kr.max_iters = chunk
-            kr.restart = min(kr.restart, chunk)
-            st = self._state()
-            code = L.check(self._lib.sem_ns_solve(d.ctx, C.byref(st), self._out.data_ptr(), self._x.data_ptr(),
-                                                  C.byref(kr), self._work.data_ptr(), self._work.numel(), d.stream),
-                           "sem_ns_solve")
-            self.krylov_iters.append(kr.iters)
-            if code == 0 or not (kr.resnorm < 0.95 * prev):
-                break
-            prev = kr.resnorm
+        kr.atol = max(kr.atol, rtol * rhs_norm)
+        st = self._state()
+        code = L.check(self._lib.sem_ns_solve(d.ctx, C.byref(st), self._out.data_ptr(), self._x.data_ptr(), C.byref(kr),
+                                              self._work.data_ptr(), self._work.numel(), d.stream), "sem_ns_solve")
+        self.last_iters, self.last_resnorm = kr.iters, kr.resnorm
+        self.krylov_iters.append(kr.iters)
+        if code != 0:
+            raise RuntimeError(f'NavierStokes LGMRES: Failed to converge in {kr.iters} iterations')
         return tuple(d.to_host(self._x[k]) for k in range(3))
 
     def _get_solution(self, T, u0=None, v0=None, p0=None):

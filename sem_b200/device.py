@@ -313,7 +313,8 @@ class SemDevice:
                 R = 0.5 * (R + R.T)
             else:
                 R = K
-            dirs.append(dict(K=K, M=M, R=R, n=n, lf=lf, a=a, tinv=tinv, tcp=tcp, Mh=Mh))
+            glf = (G.T @ torch.from_numpy(lf).to(G.device)).cpu().numpy()       # G1^T lf: enters the velocity part of the null vector
+            dirs.append(dict(K=K, M=M, R=R, n=n, lf=lf, a=a, tinv=tinv, tcp=tcp, Mh=Mh, glf=glf))
         X_, Y_ = dirs
         self._set_plan(1, X_["K"], X_["M"], (0, X_["n"]), Y_["K"], Y_["M"], (0, Y_["n"]), 0)
         if two_level:
@@ -333,6 +334,27 @@ class SemDevice:
         L.check(self.lib.sem_ctx_set_ns_schur(self.ctx, C.byref(desc)), "sem_ctx_set_ns_schur")
         self.has_ns_schur = True
         self.ns_singular = singular
+        self._ns_null_1d = (lcx, lcy, X_["glf"], Y_["glf"], X_["Mh"], Y_["Mh"])
+
+    def ns_left_null_vector(self):
+        """The left null vector l = (l_u, l_v, l_c) of the singular NS Jacobian as three device vectors, or None when the
+        Jacobian is regular.  It is separable and independent of the linearisation point: l_c = lfx (x) lfy,
+        l_u = -(G1x^T lfx) (x) (M1y lfy), l_v = -(M1x lfx) (x) (G1y^T lfy) (non-zero on the W/E resp. S/N walls only)
+        -- pinned against the sparse-LU null vector of the CPU restatement in tests/test_oracle.py."""
+        if not self.has_ns_schur:
+            raise L.SemError("ns_left_null_vector needs setup_ns_schur")
+        if not self.ns_singular:
+            return None
+        lfx, lfy, gx, gy, Mx, My = self._ns_null_1d
+        NXg, NY = lfx.size, lfy.size
+        bnd = np.zeros((NXg, NY), dtype=bool)
+        bnd[0], bnd[-1], bnd[:, 0], bnd[:, -1] = True, True, True, True
+        fields = (np.where(bnd, -np.outer(gx, My * lfy), 0.0), np.where(bnd, -np.outer(Mx * lfx, gy), 0.0), np.outer(lfx, lfy))
+        out = self.zeros(3)
+        for k, f in enumerate(fields):
+            f = f.ravel() if self.part is None else self.part.local_slice(f.ravel())
+            self.to_device(f, out[k])
+        return out
 
     def fdm_apply(self, slot, r, z, nf=1):
         L.check(self.lib.sem_fdm_apply(self.ctx, int(slot), r.data_ptr(), z.data_ptr(), int(nf), self.stream), "sem_fdm_apply")

@@ -204,6 +204,16 @@ def test_null_vector_structure_and_member_selection():
     model = np.outer(one_minus_LP, one_minus_LP).ravel()
     c = (model @ lc) / (model @ model)
     assert np.linalg.norm(lc - c * model) < 1e-10 * np.linalg.norm(lc)
+    # (1b) the whole null vector is separable: l_u = -(G1^T f) (x) (M1 f), l_v = -(M1 f) (x) (G1^T f) on the walls, f = 1 - L_P
+    # (what SemDevice.ns_left_null_vector builds for the range projection of the coupled drivers)
+    from oracle.ns_precond import Dir1D
+    d1 = Dir1D(P, ne, 1.0 / ne)
+    mb = ns._mask_bound.reshape(n1, n1)
+    lu = np.where(mb, -np.outer(d1.G.T @ d1.lfac, d1.M * d1.lfac), 0.0)
+    lv = np.where(mb, -np.outer(d1.M * d1.lfac, d1.G.T @ d1.lfac), 0.0)
+    lm = np.hstack((lu.ravel(), lv.ravel(), np.outer(d1.lfac, d1.lfac).ravel()))
+    assert np.linalg.norm(J.T @ lm) < 1e-12 * np.linalg.norm(lm)
+    assert np.linalg.norm(l - lm * (lm @ l) / (lm @ lm)) < 1e-10 * np.linalg.norm(l)
     b = -np.hstack((ru, rv, rc))
     x_ref = np.hstack(ns._get_update(-ru, -rv, -rc))
     Mp = ns._M.copy(); Mp[ns._pin] = 1.0
