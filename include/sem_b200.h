@@ -163,6 +163,14 @@ int sem_mass_diag(sem_ctx *ctx, double *m, void *stream);                       
 int sem_gather_scatter(sem_ctx *ctx, const double *elem, double *y, void *stream);
 int sem_scatter(sem_ctx *ctx, const double *x, double *elem, void *stream);
 
+/* ---- interpolation: SEM.eval_interpolation (SEM.py:248-273) on an ij-meshgrid of nxp x nyp points; also the mesh-to-mesh
+ * transfer `change_inputs` of the OpenMDAO components (CD_Component.py:23-36, NS_Component.py:23-33).  mx[nxp] / ny[nyp]:
+ * GLOBAL element column / row of every plot column / row (SEM.x2xi, SEM.py:23-36); Sx [nxp][P+1] / Sy [nyp][P+1]: the Lagrange
+ * basis values there (GLL.standard_evaluation_matrix, GLL.py:105-116); out [nxp][nyp].  All DEVICE pointers.  On a partitioned
+ * context every rank receives the whole array (the slabs' contributions are summed with ncclAllReduce). */
+int sem_interpolate(sem_ctx *ctx, const double *vec, int nxp, const int *mx, const double *Sx, int nyp, const int *ny,
+                    const double *Sy, double *out, void *stream);
+
 /* ---- convection-diffusion: CD._get_residuals / _calc_jacobians / _get_dresiduals (CD:73-121) ------------------- */
 int sem_cd_residual(sem_ctx *ctx, const sem_cd_state *st, const double *T, double *res, void *stream);
 int sem_cd_jacobians(sem_ctx *ctx, double Pe, const double *T, double *gxT, double *gyT, void *stream);

@@ -211,10 +211,7 @@ class ConvectionDiffusionSolver:
         """Interpolation of the global vector f at plotting points  (CD:180-188)."""
         d = self._dev
         xs, ys = np.asarray(points_plot[0])[:, 0], np.asarray(points_plot[1])[0, :]     # ij-meshgrid, as SEM.py:262-263
-        if d.part is None:
-            return d.interpolate(d.to_device(f, self._buf[3]), xs, ys)
-        f_e = d.scatter(d.to_device(f, self._buf[3])).cpu().numpy()
-        return SEM.eval_interpolation(f_e, self.points_e, points_plot)
+        return d.interpolate(d.to_device(f, self._buf[3]), xs, ys)
 
     def run(self, u_func, v_func, points_plot):
         """Solution at plotting points  (CD:190-203)."""

@@ -60,7 +60,10 @@ class NavierStokesSolver:
         self._x = d.zeros(3)
         self._restart = restart
         if precond == 'auto':
-            precond = 'full'
+            # the reference's own meshes (a few thousand nodes) are launch-latency bound: the ~70 extra launches of the two-level
+            # Schur stages cost more than the iterations they save there (C2: 0.79 s / 3969 its with 'fdm', 1.21 s / 1634 its with
+            # 'full'); from ~10^5 nodes on the mesh-independent iteration count wins (profiles/README.md)
+            precond = 'full' if self.N >= 30000 and P >= 2 else 'fdm'
         self._precond = {'jacobi': 1, 'fdm': 2, 'fdm+bb': 3, 'full': 4}[precond]
         self._work = None
         self._null = None            # left null vector of the Jacobian (coupled drivers: _get_update_inexact)
@@ -314,10 +317,7 @@ class NavierStokesSolver:
         """Interpolation of the global vector f at plotting points  (NS:280-288)."""
         d = self._dev
         xs, ys = np.asarray(points_plot[0])[:, 0], np.asarray(points_plot[1])[0, :]     # ij-meshgrid, as SEM.py:262-263
-        if d.part is None:
-            return d.interpolate(d.to_device(f, self._in[3]), xs, ys)
-        f_e = d.scatter(d.to_device(f, self._in[3])).cpu().numpy()
-        return SEM.eval_interpolation(f_e, self.points_e, points_plot)
+        return d.interpolate(d.to_device(f, self._in[3]), xs, ys)
 
     def run(self, T_func, points_plot):
         """Solution at plotting points  (NS:290-303)."""

@@ -80,6 +80,7 @@ SIGNATURES = {
     "sem_mass_diag": (C.c_int, [_P, _P, _P]),
     "sem_gather_scatter": (C.c_int, [_P, _P, _P, _P]),
     "sem_scatter": (C.c_int, [_P, _P, _P, _P]),
+    "sem_interpolate": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     "sem_cd_residual": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P]),
     "sem_cd_jacobians": (C.c_int, [_P, C.c_double, _P, _P, _P, _P]),
     "sem_cd_jvp": (C.c_int, [_P, C.POINTER(sem_cd_state), _P, _P, _P, _P, _P]),

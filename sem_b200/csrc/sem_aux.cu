@@ -510,4 +510,37 @@ int aux_sub(const double* a, const double* b, double* out, long long n, cudaStre
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-product interpolation (SEM.eval_interpolation, SEM.py:248-273; the mesh-to-mesh transfer `change_inputs` of the
+// OpenMDAO components, CD_Component.py:23-36): out[a][b] = sum_ij Sx[a][i] Sy[b][j] f[(mx[a] - m0) P + i][ny[b] P + j] for the
+// plot columns a whose element column mx[a] (GLOBAL index, from x2xi SEM.py:23-36) lies in this slab, 0 for the others (a
+// partitioned mesh sums the ranks' arrays).  One thread per output value, fixed summation order.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_interpolate(const MeshDev g, const double* __restrict__ f, int nxp, const int* __restrict__ mx,
+                              const double* __restrict__ Sx, int nyp, const int* __restrict__ ny, const double* __restrict__ Sy,
+                              double* __restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = blockIdx.y;
+    if (b >= nyp) return;
+    const int n1 = g.P + 1;
+    const int m = mx[a] - g.gx0 / g.P;
+    double val = 0.0;
+    if (m >= 0 && m < g.nex) {
+        const double* base = f + (size_t)(m * g.P) * g.LD + (size_t)ny[b] * g.P;
+        for (int i = 0; i < n1; ++i) {
+            double row = 0.0;
+            for (int j = 0; j < n1; ++j) row = fma(Sy[b * n1 + j], base[(size_t)i * g.LD + j], row);
+            val = fma(Sx[a * n1 + i], row, val);
+        }
+    }
+    out[(size_t)a * nyp + b] = val;
+}
+int aux_interpolate(const MeshDev& g, const double* f, int nxp, const int* mx, const double* Sx, int nyp, const int* ny,
+                    const double* Sy, double* out, cudaStream_t st) {
+    if (nxp <= 0 || nyp <= 0) return 0;
+    k_interpolate<<<dim3((unsigned)((nyp + 127) / 128), (unsigned)nxp), 128, 0, st>>>(g, f, nxp, mx, Sx, nyp, ny, Sy, out);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace semb

@@ -71,6 +71,9 @@ int aux_ns_jacobi(const MeshDev& g, const double* dK, const double* gxu, const d
 int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double* div, double* zp, int pin_gx,
                       int pin_iy, cudaStream_t st);
 
+// SEM.eval_interpolation on an ij-meshgrid (SEM.py:248-273): see k_interpolate
+int aux_interpolate(const MeshDev& g, const double* f, int nxp, const int* mx, const double* Sx, int nyp, const int* ny,
+                    const double* Sy, double* out, cudaStream_t st);
 // out = a - b
 int aux_sub(const double* a, const double* b, double* out, long long n, cudaStream_t st);
 

@@ -554,6 +554,19 @@ extern "C" int sem_scatter(sem_ctx* c, const double* x, double* elem, void* stre
     return aux_scatter(c->g, x, elem, (cudaStream_t)stream);
 }
 
+// SEM.eval_interpolation (SEM.py:248-273) of a device vector on an ij-meshgrid: mx[nxp] / ny[nyp] = element of every plot
+// column / row (x2xi, SEM.py:23-36), Sx [nxp][P+1] / Sy [nyp][P+1] = GLL.standard_evaluation_matrix (GLL.py:105-116), all
+// DEVICE arrays; out [nxp][nyp] DEVICE.  On a partitioned mesh every rank evaluates the plot columns inside its slab and the
+// arrays are summed over the ranks (ncclAllReduce): every rank returns the whole result.
+extern "C" int sem_interpolate(sem_ctx* c, const double* vec, int nxp, const int* mx, const double* Sx, int nyp, const int* ny,
+                               const double* Sy, double* out, void* stream) {
+    SEM_CHECK_CTX(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aux_interpolate(c->g, vec, nxp, mx, Sx, nyp, ny, Sy, out, st)) return -1;
+    if (c->has_comm) return comm_allreduce_sum(c->comm, out, nxp * nyp, st);
+    return 0;
+}
+
 // ---- convection-diffusion ---------------------------------------------------------------------------------------
 extern "C" int sem_cd_residual(sem_ctx* c, const sem_cd_state* s, const double* T, double* res, void* stream) {
     SEM_CHECK_CTX(c);
@@ -756,7 +769,7 @@ extern "C" int sem_ctx_set_fdm(sem_ctx* c, int slot, const sem_fdm_dir* x, const
     d.s1 = std::max(x->lo, g.has_left ? 1 : 0);               // the interface line is summed from the left rank's copy
     d.k1 = x->lo + x->cnt - d.s1;
     d.k1p = round_up(d.k1, 16);
-    if (fdm_dir_build(d.y, y->lo, y->cnt, y->fold, y->Qe, y->Qo, y->lam)) return -1;
+    if (fdm_dir_build(d.y, y->lo, y->cnt, y->fold, y->Qe, y->Qo, y->lam, 128)) return -1;
     d.cols = std::max(round_up(y->cnt, 128), d.y.nep + d.y.nop);
     auto zalloc = [](double** p, size_t n) -> int {
         SEM_CUDA(cudaMalloc(p, sizeof(double) * n));
@@ -793,13 +806,13 @@ static int fdm_dist_apply(sem_ctx* c, sem_ctx::FdmDist& d, const double* r, doub
     if (fdm_fold_x(x1, d.y.lo, d.y.cnt, r, 0, g.LD, d.R, d.cols, 0, 1, st)) return -1;
     GemmArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.nprob = 1; a.batch = 1;
+    a.nprob = 1; a.batch = 1; a.tile = 128;
     a.p[0] = GemmProblem{d.QxT, d.R, d.T, d.k1p, d.cols, d.cols, 0, 0, 0, d.modesP, ycols, d.k1p, nullptr, nullptr};
     if (gemm_launch(a, EPI_NONE, st)) return -1;
     if (comm_reduce_scatter_sum(c->comm, d.T, d.mA, (size_t)d.B * d.cols, st)) return -1;
     if (fdm_fold_y(d.y, d.mA, d.mB, d.B, d.cols, 0, 1, st)) return -1;
-    if (fdm_step_y(d.y, false, d.mB, d.mA, d.B, d.cols, 0, d.lamx + (size_t)c->comm.rank * d.B, d.den_floor, 1, st)) return -1;
-    if (fdm_step_y(d.y, true, d.mA, d.mB, d.B, d.cols, 0, nullptr, 0.0, 1, st)) return -1;
+    if (fdm_step_y(d.y, false, d.mB, d.mA, d.B, d.cols, 0, d.lamx + (size_t)c->comm.rank * d.B, d.den_floor, 1, 128, st)) return -1;
+    if (fdm_step_y(d.y, true, d.mA, d.mB, d.B, d.cols, 0, nullptr, 0.0, 1, 128, st)) return -1;
     if (fdm_unfold_y(d.y, d.mB, d.mA, d.B, d.cols, 0, 1, st)) return -1;
     if (comm_allgather(c->comm, d.mA, d.T, (size_t)d.B * d.cols, st)) return -1;
     a.p[0] = GemmProblem{d.Qx, d.T, d.X, d.modesP, d.cols, d.cols, 0, 0, 0, d.m4p, ycols, d.modesP, nullptr, nullptr};

@@ -26,87 +26,107 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm(const __grid_constant__ GemmArgs g) {
+// CF: tile configuration -- BM x BN CTA tile, WM x WN warp tile (multiples of 8), BK = 16, STAGES-deep cp.async ring.
+//   GemmBig  : 128 x 128, warps 32 x 64 (8 warps, 64 accumulators per thread)  -- large transforms, one CTA per SM
+//   GemmMid  :  64 x  64, warps 32 x 32 (4 warps)  -- a few hundred nodes per direction: enough CTAs to fill the SMs
+//   GemmSmall:  32 x  32, warps 16 x 16 (4 warps)  -- the reference's own meshes (65 x 65 nodes): a 128-wide tile would pad a
+//               32 x 63 x 32 product 32-fold and leave it to ONE SM (24-40 us per launch in the round-2 launch list)
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, BK = 16;
+    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN, THREADS = 32 * WARPS_M * WARPS_N;
+    static constexpr int FM = WM / 8, FN = WN / 8;
+    static constexpr int LDA = BK + 4;      // = 4 (mod 16): conflict-free LDS.64 fragment loads
+    static constexpr int LDB = BN + 4;      // = 4 (mod 16) for BN a multiple of 16
+    static constexpr int A_CHUNKS = BM * BK / 2, B_CHUNKS = BK * BN / 2;   // 16-byte chunks per stage
+    static constexpr size_t SMEM = (size_t)STAGES * (BM * LDA + BK * LDB) * sizeof(double);
+    static_assert(A_CHUNKS % THREADS == 0 && B_CHUNKS % THREADS == 0, "tile loads must divide evenly over the threads");
+};
+using GemmBig = GemmCfg<128, 128, 32, 64, 4>;
+using GemmMid = GemmCfg<64, 64, 32, 32, 3>;
+using GemmSmall = GemmCfg<32, 32, 16, 16, 3>;
+
+template <class CF, int EPI>
+__global__ void __launch_bounds__(CF::THREADS, 1) k_dgemm(const __grid_constant__ GemmArgs g) {
     extern __shared__ __align__(16) double gsm[];
     const int prob = blockIdx.z % g.nprob, bat = blockIdx.z / g.nprob;
     const GemmProblem& q = g.p[prob];
-    const int bm = blockIdx.y * GM_BM, bn = blockIdx.x * GM_BN;
+    const int bm = blockIdx.y * CF::BM, bn = blockIdx.x * CF::BN;
     if (bm >= q.M || bn >= q.N) return;
     double* sA = gsm;
-    double* sB = gsm + GM_STAGES * GM_BM * GM_LDA;
+    double* sB = gsm + CF::STAGES * CF::BM * CF::LDA;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
+    const int wm = (warp / CF::WARPS_N) * CF::WM, wn = (warp % CF::WARPS_N) * CF::WN;
     const double* __restrict__ Ag = q.A + bat * q.sA + (size_t)bm * q.lda;
     const double* __restrict__ Bg = q.B + bat * q.sB + bn;
-    const int KT = q.K / GM_BK;
+    const int KT = q.K / CF::BK;
 
     auto load = [&](int stage, int kt) {
-        const double* a = Ag + kt * GM_BK;
-        const double* b = Bg + (size_t)kt * GM_BK * q.ldb;
-        double* da = sA + stage * GM_BM * GM_LDA;
-        double* db = sB + stage * GM_BK * GM_LDB;
+        const double* a = Ag + kt * CF::BK;
+        const double* b = Bg + (size_t)kt * CF::BK * q.ldb;
+        double* da = sA + stage * CF::BM * CF::LDA;
+        double* db = sB + stage * CF::BK * CF::LDB;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = tid + i * GM_THREADS;
-            const int r = c >> 3, h = c & 7;
-            cp_async16(da + r * GM_LDA + h * 2, a + (size_t)r * q.lda + h * 2);
+        for (int i = 0; i < CF::A_CHUNKS / CF::THREADS; ++i) {
+            const int c = tid + i * CF::THREADS;
+            const int r = c / (CF::BK / 2), h = c % (CF::BK / 2);
+            cp_async16(da + r * CF::LDA + h * 2, a + (size_t)r * q.lda + h * 2);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = tid + i * GM_THREADS;
-            const int r = c >> 6, h = c & 63;
-            cp_async16(db + r * GM_LDB + h * 2, b + (size_t)r * q.ldb + h * 2);
+        for (int i = 0; i < CF::B_CHUNKS / CF::THREADS; ++i) {
+            const int c = tid + i * CF::THREADS;
+            const int r = c / (CF::BN / 2), h = c % (CF::BN / 2);
+            cp_async16(db + r * CF::LDB + h * 2, b + (size_t)r * q.ldb + h * 2);
         }
     };
 
-    double acc[4][8][2];
+    double acc[CF::FM][CF::FN][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < CF::FM; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < CF::FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
-    for (int s = 0; s < GM_STAGES - 1; ++s) {
+    for (int s = 0; s < CF::STAGES - 1; ++s) {
         if (s < KT) load(s, s);
         cp_async_commit();
     }
     const int arow = wm + (lane >> 2), acol = lane & 3;
     const int brow = lane & 3, bcol = wn + (lane >> 2);
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<GM_STAGES - 2>();
+        cp_async_wait<CF::STAGES - 2>();
         __syncthreads();
         {   // refill the stage consumed in the previous trip
-            const int nk = kt + GM_STAGES - 1;
-            if (nk < KT) load(nk % GM_STAGES, nk);
+            const int nk = kt + CF::STAGES - 1;
+            if (nk < KT) load(nk % CF::STAGES, nk);
             cp_async_commit();
         }
-        const int st = kt % GM_STAGES;
-        const double* a = sA + st * GM_BM * GM_LDA + arow * GM_LDA + acol;
-        const double* b = sB + st * GM_BK * GM_LDB + brow * GM_LDB + bcol;
+        const int st = kt % CF::STAGES;
+        const double* a = sA + st * CF::BM * CF::LDA + arow * CF::LDA + acol;
+        const double* b = sB + st * CF::BK * CF::LDB + brow * CF::LDB + bcol;
 #pragma unroll
-        for (int k4 = 0; k4 < GM_BK / 4; ++k4) {
-            double af[4], bf[8];
+        for (int k4 = 0; k4 < CF::BK / 4; ++k4) {
+            double af[CF::FM], bf[CF::FN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = a[i * 8 * GM_LDA + k4 * 4];
+            for (int i = 0; i < CF::FM; ++i) af[i] = a[i * 8 * CF::LDA + k4 * 4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = b[k4 * 4 * GM_LDB + j * 8];
+            for (int j = 0; j < CF::FN; ++j) bf[j] = b[k4 * 4 * CF::LDB + j * 8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < CF::FM; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma(acc[i][j], af[i], bf[j]);
+                for (int j = 0; j < CF::FN; ++j) dmma(acc[i][j], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
 
     double* __restrict__ Cg = q.C + bat * q.sC;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CF::FM; ++i) {
         const int row = bm + wm + i * 8 + (lane >> 2);
         double lxr = 0.0;
         if constexpr (EPI == EPI_SCALE) lxr = q.lx[row];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CF::FN; ++j) {
             const int col = bn + wn + j * 8 + 2 * (lane & 3);
             double v0 = acc[i][j][0], v1 = acc[i][j][1];
             if constexpr (EPI == EPI_SCALE) {
@@ -119,29 +139,37 @@ __global__ void __launch_bounds__(GM_THREADS, 1) k_dgemm(const __grid_constant__
     }
 }
 
-int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
+template <class CF>
+static int gemm_launch_cfg(const GemmArgs& a, int epi, int maxM, int maxN, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        SEM_CUDA(cudaFuncSetAttribute(k_dgemm<EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
-        SEM_CUDA(cudaFuncSetAttribute(k_dgemm<EPI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
+        SEM_CUDA(cudaFuncSetAttribute(k_dgemm<CF, EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
+        SEM_CUDA(cudaFuncSetAttribute(k_dgemm<CF, EPI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
         configured = true;
     }
-    int maxM = 0, maxN = 0;
+    dim3 grid((unsigned)(maxN / CF::BN), (unsigned)(maxM / CF::BM), (unsigned)(a.nprob * a.batch));
+    if (epi == EPI_SCALE) k_dgemm<CF, EPI_SCALE><<<grid, CF::THREADS, CF::SMEM, st>>>(a);
+    else k_dgemm<CF, EPI_NONE><<<grid, CF::THREADS, CF::SMEM, st>>>(a);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
+    int maxM = 0, maxN = 0, tile = a.tile;
+    if (tile != 32 && tile != 64 && tile != 128) { set_error("gemm_launch: tile must be 32, 64 or 128"); return -2; }
     for (int i = 0; i < a.nprob; ++i) {
         const GemmProblem& q = a.p[i];
-        if (q.M % GM_BM || q.N % GM_BN || q.K % GM_BK || q.K <= 0 || (q.lda & 1) || (q.ldb & 1) || (q.ldc & 1)) {
-            set_error("gemm_launch: dimensions must be padded (M, N to 128, K to 16, even leading dimensions)");
+        if (q.M % tile || q.N % tile || q.K % 16 || q.K <= 0 || (q.lda & 1) || (q.ldb & 1) || (q.ldc & 1)) {
+            set_error("gemm_launch: dimensions must be padded (M, N to the tile, K to 16, even leading dimensions)");
             return -2;
         }
         maxM = std::max(maxM, q.M);
         maxN = std::max(maxN, q.N);
     }
     if (a.nprob < 1 || maxM == 0 || maxN == 0) return 0;
-    dim3 grid((unsigned)(maxN / GM_BN), (unsigned)(maxM / GM_BM), (unsigned)(a.nprob * a.batch));
-    if (epi == EPI_SCALE) k_dgemm<EPI_SCALE><<<grid, GM_THREADS, GM_SMEM, st>>>(a);
-    else k_dgemm<EPI_NONE><<<grid, GM_THREADS, GM_SMEM, st>>>(a);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
+    if (tile == 128) return gemm_launch_cfg<GemmBig>(a, epi, maxM, maxN, st);
+    if (tile == 64) return gemm_launch_cfg<GemmMid>(a, epi, maxM, maxN, st);
+    return gemm_launch_cfg<GemmSmall>(a, epi, maxM, maxN, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -248,7 +276,8 @@ __global__ void k_unfold_x(const double* __restrict__ src, int ld, long long sst
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static int pad128(int v) { return v > 0 ? round_up(v, 128) : 0; }
+// Padding unit of the transform buffers: 128 (the big GEMM tile) for large directions, 32 (the small tile) below GM_SMALL_MAX.
+static int padu(int v, int unit) { return v > 0 ? round_up(v, unit) : 0; }
 
 void fdm_dir_free(FdmDir& d) {
     if (d.Qe) cudaFree(d.Qe);
@@ -277,15 +306,17 @@ __global__ void k_pad_square(const double* __restrict__ src, int n, double* __re
     dstT[(size_t)j * np + i] = v;
 }
 
-int fdm_dir_build(FdmDir& d, int lo, int cnt, int fold, const double* Qe, const double* Qo, const double* lam) {
+int fdm_tile_for(int n) { return n >= 1024 ? 128 : (n >= 200 ? 64 : 32); }
+
+int fdm_dir_build(FdmDir& d, int lo, int cnt, int fold, const double* Qe, const double* Qo, const double* lam, int tile) {
     std::memset(&d, 0, sizeof(d));
     d.lo = lo;
     d.cnt = cnt;
     d.fold = fold;
     d.ne = fold ? (cnt + 1) / 2 : cnt;
     d.no = fold ? cnt / 2 : 0;
-    d.nep = pad128(d.ne);
-    d.nop = pad128(d.no);
+    d.nep = padu(d.ne, tile);
+    d.nop = padu(d.no, tile);
     auto square = [&](const double* src, int n, int np, double** Q, double** QT) -> int {
         if (n == 0) return 0;
         SEM_CUDA(cudaMalloc(Q, sizeof(double) * (size_t)np * np));
@@ -314,12 +345,13 @@ int fdm_plan_build(FdmPlan& p, const MeshDev& g, int xlo, int xcnt, int xfold, c
         set_error("fdm_plan_build: active range outside the mesh");
         return -2;
     }
-    if (fdm_dir_build(p.x, xlo, xcnt, xfold, Qxe, Qxo, lamx)) return -1;
-    if (fdm_dir_build(p.y, ylo, ycnt, yfold, Qye, Qyo, lamy)) return -1;
+    p.tile = fdm_tile_for(std::min(xcnt, ycnt));
+    if (fdm_dir_build(p.x, xlo, xcnt, xfold, Qxe, Qxo, lamx, p.tile)) return -1;
+    if (fdm_dir_build(p.y, ylo, ycnt, yfold, Qye, Qyo, lamy, p.tile)) return -1;
     p.outside = outside;
     p.den_floor = den_floor;
     p.rows = p.x.nep + p.x.nop;
-    p.cols = std::max(pad128(ycnt), p.y.nep + p.y.nop);
+    p.cols = std::max(padu(ycnt, p.tile), p.y.nep + p.y.nop);
     p.nbuf = nbuf;
     const size_t bytes = sizeof(double) * (size_t)nbuf * p.rows * p.cols;
     SEM_CUDA(cudaMalloc(&p.bufA, bytes));
@@ -367,11 +399,12 @@ static int step_x(const FdmPlan& p, bool transposed, const double* src, double* 
                                 p.x.nop, p.cols, p.cols, 0, fs, fs, p.x.nop, ncols, p.x.nop, nullptr, nullptr};
     a.nprob = np;
     a.batch = nf;
+    a.tile = p.tile;
     return gemm_launch(a, EPI_NONE, st);
 }
 
 int fdm_step_y(const FdmDir& y, bool transposed, const double* src, double* dst, int rows, int ld, long long fs, const double* lx,
-               double den_floor, int nf, cudaStream_t st) {
+               double den_floor, int nf, int tile, cudaStream_t st) {
     GemmArgs a;
     std::memset(&a, 0, sizeof(a));
     int np = 0;
@@ -382,6 +415,7 @@ int fdm_step_y(const FdmDir& y, bool transposed, const double* src, double* dst,
                                 y.nop, y.nop, lx, lx ? y.lam + y.nep : nullptr};
     a.nprob = np;
     a.batch = nf;
+    a.tile = tile;
     a.den_floor = den_floor;
     return gemm_launch(a, lx ? EPI_SCALE : EPI_NONE, st);
 }
@@ -390,12 +424,12 @@ int fdm_plan_apply(FdmPlan& p, const MeshDev& g, const double* r, double* z, int
     if (!p.ready) { set_error("fdm_plan_apply: plan not built"); return -2; }
     if (nf > p.nbuf) { set_error("fdm_plan_apply: more fields than work buffers"); return -2; }
     const long long fs = (long long)p.rows * p.cols;
-    const int ycols = pad128(p.y.cnt);
+    const int ycols = padu(p.y.cnt, p.tile);
     if (fdm_fold_x(p.x, p.y.lo, p.y.cnt, r, stride, g.LD, p.bufA, p.cols, fs, nf, st)) return -1;   // r -> A (x-folded node space)
     if (step_x(p, true, p.bufA, p.bufB, ycols, nf, st)) return -1;                                   // B = Qx^T A  (x modes, y nodes)
     if (fdm_fold_y(p.y, p.bufB, p.bufA, p.rows, p.cols, fs, nf, st)) return -1;
-    if (fdm_step_y(p.y, false, p.bufA, p.bufB, p.rows, p.cols, fs, p.x.lam, p.den_floor, nf, st)) return -1;   // B = (A Qy) / (lx + ly)
-    if (fdm_step_y(p.y, true, p.bufB, p.bufA, p.rows, p.cols, fs, nullptr, 0.0, nf, st)) return -1;            // A = B Qy^T
+    if (fdm_step_y(p.y, false, p.bufA, p.bufB, p.rows, p.cols, fs, p.x.lam, p.den_floor, nf, p.tile, st)) return -1;   // B = (A Qy) / (lx + ly)
+    if (fdm_step_y(p.y, true, p.bufB, p.bufA, p.rows, p.cols, fs, nullptr, 0.0, nf, p.tile, st)) return -1;    // A = B Qy^T
     if (fdm_unfold_y(p.y, p.bufA, p.bufB, p.rows, p.cols, fs, nf, st)) return -1;
     if (step_x(p, false, p.bufB, p.bufA, ycols, nf, st)) return -1;                                  // A = Qx B (x-folded node space)
     return fdm_unfold_x(p.x, p.y.lo, p.y.cnt, p.bufA, p.cols, fs, r, z, stride, g, p.outside, nf, st);

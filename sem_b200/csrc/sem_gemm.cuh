@@ -11,12 +11,7 @@
 
 namespace semb {
 
-constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_STAGES = 4, GM_THREADS = 256;
-constexpr int GM_LDA = GM_BK + 4;     // A tile [BM][LDA]: 20 = 4 (mod 16) -> conflict-free LDS.64 fragment loads
-constexpr int GM_LDB = GM_BN + 4;     // B tile [BK][LDB]: 132 = 4 (mod 16)
-constexpr size_t GM_SMEM = (size_t)GM_STAGES * (GM_BM * GM_LDA + GM_BK * GM_LDB) * sizeof(double);
-
-// C[M][N] = A[M][K] B[K][N], all row-major.  M, N multiples of 128, K a multiple of 16 (operands are zero padded internal
+// C[M][N] = A[M][K] B[K][N], all row-major.  M, N multiples of the CTA tile (128 / 64 / 32), K a multiple of 16 (operands are zero padded internal
 // buffers), leading dimensions even, pointers 16-byte aligned.  Up to GM_MAXP independent problems per launch (the even and
 // the odd half of a folded transform), each repeated `batch` times with the given strides (fields).
 constexpr int GM_MAXP = 2;
@@ -31,6 +26,7 @@ struct GemmProblem {
 struct GemmArgs {
     GemmProblem p[GM_MAXP];
     int nprob, batch;
+    int tile;                // CTA tile of the kernel variant: 128, 64 or 32 (M and N of every problem are multiples of it)
     double den_floor;        // EPI_SCALE: denominators <= den_floor give 0
 };
 enum { EPI_NONE = 0, EPI_SCALE = 1 };
@@ -47,7 +43,7 @@ struct FdmDir {
     int lo, cnt;            // active node range
     int fold;               // parity-split direction
     int ne, no;             // even / odd part sizes (fold: ceil(cnt/2), floor(cnt/2); else cnt, 0) == number of even / odd modes
-    int nep, nop;           // padded to multiples of 128 (0 stays 0)
+    int nep, nop;           // padded to multiples of the plan's GEMM tile (0 stays 0)
     double *Qe, *QeT;       // [nep][nep] row-major: Qe[node][mode], QeT[mode][node], zero padded
     double *Qo, *QoT;       // [nop][nop]
     double* lam;            // [nep + nop]: even modes, then odd modes; padding 0
@@ -55,6 +51,7 @@ struct FdmDir {
 struct FdmPlan {
     FdmDir x, y;
     int outside;            // 1: z = r outside the active range, 0: z = 0
+    int tile;               // GEMM tile / padding unit: 128 for large meshes, 64 / 32 for small ones (fdm_tile_for)
     int rows, cols;         // padded buffer shape: rows = x.nep + x.nop, cols = max(round_up(y.cnt, 128), y.nep + y.nop)
     int nbuf;               // fields the work buffers hold
     double *bufA, *bufB;    // [nbuf][rows][cols] ping-pong work buffers (zero initialised; pads stay zero)
@@ -62,7 +59,8 @@ struct FdmPlan {
     int ready;
 };
 int fdm_plan_free(FdmPlan& p);
-int fdm_dir_build(FdmDir& d, int lo, int cnt, int fold, const double* Qe, const double* Qo, const double* lam);
+int fdm_tile_for(int n);
+int fdm_dir_build(FdmDir& d, int lo, int cnt, int fold, const double* Qe, const double* Qo, const double* lam, int tile);
 void fdm_dir_free(FdmDir& d);
 // building blocks, also used by the distributed (partitioned) variant in sem_capi.cu: buffers are [rows][ld], `fs` doubles
 // between the nf fields
@@ -74,7 +72,7 @@ int fdm_fold_y(const FdmDir& y, const double* src, double* dst, int rows, int ld
 int fdm_unfold_y(const FdmDir& y, const double* src, double* dst, int rows, int ld, long long fs, int nf, cudaStream_t st);
 // dst[rows][part] = src[rows][part] Q(part) (transposed: Q^T); lx != null: spectral scaling 1 / (lx[row] + ly[col])
 int fdm_step_y(const FdmDir& y, bool transposed, const double* src, double* dst, int rows, int ld, long long fs, const double* lx,
-               double den_floor, int nf, cudaStream_t st);
+               double den_floor, int nf, int tile, cudaStream_t st);
 // Qe/Qo/lam are DEVICE arrays in the compact (unpadded) shapes [ne][ne], [no][no], [ne + no] per direction.
 int fdm_plan_build(FdmPlan& p, const MeshDev& g, int xlo, int xcnt, int xfold, const double* Qxe, const double* Qxo,
                    const double* lamx, int ylo, int ycnt, int yfold, const double* Qye, const double* Qyo, const double* lamy,

@@ -157,14 +157,23 @@ class SemDevice:
 
     # ---- tensor-product interpolation (SEM.eval_interpolation, SEM.py:248-273; mesh-to-mesh transfer of the couplers) ------
     def interpolate(self, vec, xs, ys):
-        """Values of the SEM interpolant of the device vector ``vec`` on the ij-meshgrid xs x ys: I_x F I_y^T with the 1-D
-        interpolation matrices of ``SEM.interp_matrix_1d``, two small dense products on the device.  Whole mesh only."""
+        """Values of the SEM interpolant of the device vector ``vec`` on the ij-meshgrid xs x ys (SEM.eval_interpolation,
+        SEM.py:248-273) by the tensor-product kernel ``sem_interpolate``: the element of every plot column / row comes from
+        ``x2xi`` (SEM.py:23-36) and the Lagrange basis values from ``GLL.standard_evaluation_matrix`` (GLL.py:105-116), like
+        the reference.  Works on a partitioned mesh too (every rank gets the whole array)."""
         from . import SEM
-        if self.part is not None and self.part.world > 1:
-            raise L.SemError("interpolation needs the whole mesh on one GPU")
-        Ix = torch.from_numpy(SEM.interp_matrix_1d(self.P, self.N_ex, self.dx, xs)).to(self.tdev)
-        Iy = torch.from_numpy(SEM.interp_matrix_1d(self.P, self.N_ey, self.dy, ys)).to(self.tdev)
-        return ((Ix @ vec[:, :self.NY]) @ Iy.T).cpu().numpy()
+        xs, ys = np.asarray(xs, dtype=np.float64).ravel(), np.asarray(ys, dtype=np.float64).ravel()
+        tabs = []
+        for pts, h, nel in ((xs, self.dx, self.N_ex), (ys, self.dy, self.N_ey)):
+            e, xi = SEM.x2xi(pts, h)
+            e = np.clip(e, 0, nel - 1)
+            S = GLL.standard_evaluation_matrix(self.P, xi)
+            tabs.append((torch.from_numpy(e.astype(np.int32)).to(self.tdev), torch.from_numpy(np.ascontiguousarray(S)).to(self.tdev)))
+        (mx, Sx), (ny, Sy) = tabs
+        out = torch.empty((xs.size, ys.size), dtype=torch.float64, device=self.tdev)
+        L.check(self.lib.sem_interpolate(self.ctx, vec.data_ptr(), int(xs.size), mx.data_ptr(), Sx.data_ptr(), int(ys.size),
+                                         ny.data_ptr(), Sy.data_ptr(), out.data_ptr(), self.stream), "sem_interpolate")
+        return out.cpu().numpy()
 
     # ---- fast-diagonalisation plans (sem_ctx_set_fdm) ----------------------------------------------------------------------
     _EIG_HOST_MAX = 2100     # pencils up to this size are diagonalised on the host (LAPACK), larger ones with torch on the GPU

@@ -30,7 +30,7 @@ def main():
             fails.append(f"rank {rank}: {name} = {val:.3e} (tol {tol:.0e})")
 
     # ---- CD: applies, Jacobian, solve --------------------------------------------------------------------------------
-    P, nx, ny = 4, 8, 6
+    P, nx, ny = 4, max(8, world + 1), 6          # world = 3: slabs of unequal width, a middle rank with two neighbours
     kw = dict(L_x=1.5, L_y=1.0, Pe=25.0, P=P, N_ex=nx, N_ey=ny, T_W=0.5, T_E=-0.5, T_S=0.1)
     part = Partition(nx, ny, P, rank, world)
     cd = sem_b200.ConvectionDiffusionSolver(mtol=1e-12, device=local, partition=(rank, world), **kw)
@@ -50,8 +50,9 @@ def main():
     check("cd points", float(np.abs(cd.points - np.stack([sl(cd_o.points[0]), sl(cd_o.points[1])])).max()), 1e-15)
 
     # ---- NS: applies and a Newton solve --------------------------------------------------------------------------------
-    nkw = dict(L_x=1.0, L_y=1.0, Re=50.0, Gr=200.0, P=3, N_ex=4, N_ey=4, u_N=1.0)
-    part = Partition(4, 4, 3, rank, world)
+    nex_ns = max(4, world + world % 2)
+    nkw = dict(L_x=1.0, L_y=1.0, Re=50.0, Gr=200.0, P=3, N_ex=nex_ns, N_ey=4, u_N=1.0)
+    part = Partition(nex_ns, 4, 3, rank, world)
     sl = part.local_slice
     ns = sem_b200.NavierStokesSolver(mtol=1e-13, mtol_newton=1e-13, iprint=[], device=local, partition=(rank, world), **nkw)
     ns_o = so.NSOracle(mtol=1e-13, mtol_newton=1e-13, **nkw)
@@ -70,6 +71,47 @@ def main():
     check("ns solve p", relerr(ps, sl(po)), 1e-8)
     if ns._k != ns_o._k:
         fails.append(f"rank {rank}: Newton its {ns._k} vs {ns_o._k}")
+    # run() / _get_interpol on a partitioned solver: every rank gets the whole plot array (sem_interpolate + all-reduce)
+    xp, yp = np.meshgrid(np.linspace(0, 1, 23), np.linspace(0, 1, 17), indexing='ij')
+    check("partitioned interpolation", relerr(ns._get_interpol(us, (xp, yp)), ns_o._get_interpol(uo, (xp, yp))), 1e-8)
+
+    # ---- the partitioned NS preconditioner (distributed fast-diagonalisation plans, ring Chebyshev with interface exchange,
+    #      all-reduced projector coefficients and member dots): every stage against the CPU mirror, then a Newton solve with it
+    from oracle.ns_precond import NSPrecondMirror
+    for (Pq, nxq, nyq, Re) in ((4, 2 * world, 6, 80.0), (3, nex_ns, 4, 40.0)):
+        qkw = dict(L_x=1.2, L_y=0.9, Re=Re, Gr=0.0, P=Pq, N_ex=nxq, N_ey=nyq, u_N=1.0, v_W=0.2)
+        part = Partition(nxq, nyq, Pq, rank, world)
+        sl = part.local_slice
+        nsq = sem_b200.NavierStokesSolver(mtol=1e-13, mtol_newton=1e-13, iprint=[], device=local, partition=(rank, world),
+                                          precond='full', **qkw)
+        nsq_o = so.NSOracle(mtol=1e-13, mtol_newton=1e-13, **qkw)
+        N = nsq_o.N
+        uq, vq, pq, Tq = (0.3 * rng.standard_normal(N) for _ in range(4))
+        nsq._get_residuals(sl(uq), sl(vq), sl(pq), sl(Tq))
+        nsq._calc_jacobians(sl(uq), sl(vq))
+        nsq_o._get_residuals(uq, vq, pq, Tq)
+        nsq_o._calc_jacobians(uq, vq)
+        m = NSPrecondMirror(nsq_o)
+        aa, bb = rng.standard_normal(N), rng.standard_normal(N)
+        tag = f"P{Pq} {nxq}x{nyq}"
+        ref1 = np.where(m.pin == np.arange(N), aa, m.coarse(aa))
+        check(f"{tag} coarse", relerr(nsq._precond_debug(1, 4, sl(aa)), sl(ref1)), 1e-9)
+        zin = np.where(m.inner, bb, 0.0)
+        zin[m.pin] = aa[m.pin]
+        check(f"{tag} ring", relerr(nsq._precond_debug(2, 4, sl(aa), sl(zin)), sl(m.add_ring(zin, aa))), 1e-9)
+        check(f"{tag} stokes residual", relerr(nsq._precond_debug(3, 4, sl(aa), sl(zin)), sl(aa - m.schur_stokes(zin))), 1e-9)
+        ref4 = m.pcd(aa)
+        ref4[m.pin] = aa[m.pin]
+        check(f"{tag} pcd", relerr(nsq._precond_debug(4, 4, sl(aa)), sl(ref4)), 1e-9)
+        r3 = tuple(rng.standard_normal(N) for _ in range(3))
+        for level in (2, 3, 4):
+            z3 = nsq._precond_debug(0, level, tuple(sl(x) for x in r3))
+            ref = np.split(m.apply(np.hstack(r3), level), 3)
+            check(f"{tag} precond level {level}", max(relerr(x, sl(y)) for x, y in zip(z3, ref)), 1e-9)
+        Tin = nsq_o._get_vector(lambda x, y: 0.0 * x)
+        us, vs, ps = nsq._get_solution(sl(Tin))
+        uo, vo, po = nsq_o._get_solution(Tin)
+        check(f"{tag} ns solve (full preconditioner)", max(relerr(us, sl(uo)), relerr(vs, sl(vo)), relerr(ps, sl(po))), 1e-8)
 
     # ---- larger stiffness apply: partitioned result == single-GPU result, bitwise away from / to rounding at the interface
     P, ne = 8, 16 * world
