@@ -118,7 +118,7 @@ int sem_fdm_apply(sem_ctx *ctx, int slot, const double *r, double *z, int nf, vo
 /* ---- Schur-complement stages of the NS preconditioner (sem_krylov.precond = 3, 4); replaces the diagonal-mass
  * preconditioner of NS:208-212.  All arrays are HOST pointers and are copied.
  *   wl, wr [P+1]        element-local values (1 - xn_j) L_P(xi_j), xn_j L_P(xi_j) of the coarse-space functions
- *   ta/tinv/tcp_x [N_ex+1], _y [N_ey+1]   Thomas factors of the tridiagonal Gram matrices W^T M W of the two directions
+ *   Tinv_x [(N_ex+1)^2], Tinv_y [(N_ey+1)^2]   inverses (dense, row-major) of the tridiagonal Gram matrices W^T M W
  *   lfx [NX_global], lfy [NY]             1-D factors of the pressure part l_c = lfx (x) lfy of the Jacobian's left null vector
  *   singular            the Jacobian is singular (l_c vanishes on the boundary and at the pin): apply the member correction
  *   inv_den             1 / (m_c . l_c), m_c = M_p l_c
@@ -126,7 +126,7 @@ int sem_fdm_apply(sem_ctx *ctx, int slot, const double *r, double *z, int nf, vo
  *   cheb_lo, cheb_hi, cheb_steps           spectrum bounds of the diagonally scaled ring block and polynomial degree */
 typedef struct {
     const double *wl, *wr;
-    const double *ta_x, *tinv_x, *tcp_x, *ta_y, *tinv_y, *tcp_y;
+    const double *Tinv_x, *Tinv_y;
     const double *lfx, *lfy;
     int singular, two_level;
     double inv_den;

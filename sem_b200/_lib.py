@@ -45,8 +45,7 @@ class sem_fdm_dir(C.Structure):
 
 class sem_ns_schur_desc(C.Structure):
     _fields_ = [("wl", C.c_void_p), ("wr", C.c_void_p),
-                ("ta_x", C.c_void_p), ("tinv_x", C.c_void_p), ("tcp_x", C.c_void_p),
-                ("ta_y", C.c_void_p), ("tinv_y", C.c_void_p), ("tcp_y", C.c_void_p),
+                ("Tinv_x", C.c_void_p), ("Tinv_y", C.c_void_p),
                 ("lfx", C.c_void_p), ("lfy", C.c_void_p), ("singular", C.c_int), ("two_level", C.c_int),
                 ("inv_den", C.c_double), ("cheb_lo", C.c_double), ("cheb_hi", C.c_double), ("cheb_steps", C.c_int)]
 

@@ -94,11 +94,12 @@ struct sem_ctx {
         int cheb_steps;
         double cheb_inv_theta, cheb_a[8], cheb_b[8];
         PwDir px, py;
-        double* tables;                  // one device block holding wl, wr and the Thomas factors of both directions
+        double* tables;                  // one device block holding wl, wr and the null-vector factors
+        double *TinvX, *TinvY;           // padded inverses of the projector Gram matrices: [kxp][kxp], [kyp][kyp]
+        int tile, kxp, kyp, ldx, rowsy;  // GEMM tile; padded vertex counts; pitch of cx; padded rows of cy
         double *lc, *mc;                 // l_c = lfx (x) lfy and m_c = M_p l_c as vectors
         double* w[10];                   // work vectors (zero initialised): Y, Z1, R1, G0, G1, V0, V1, NR, RHO, E
-        double *cx, *cy;                 // projector coefficients: [(N_ex + 1)][LD] and [NX][ldcy]
-        int ldcy;
+        double *cx, *cx2, *cy, *cy2;     // projector coefficients before / after T^-1: [kxp][ldx] and [rowsy][kyp]
         double* sums;                    // device [2]
     } sch;
     TabDev tab() const { return TabDev{dD, dKs, dw}; }
@@ -110,8 +111,8 @@ static void schur_free(sem_ctx::NsSchur& q) {
     if (q.mc) cudaFree(q.mc);
     for (double* p : q.w)
         if (p) cudaFree(p);
-    if (q.cx) cudaFree(q.cx);
-    if (q.cy) cudaFree(q.cy);
+    for (double* p : {q.cx, q.cx2, q.cy, q.cy2, q.TinvX, q.TinvY})
+        if (p) cudaFree(p);
     if (q.sums) cudaFree(q.sums);
     std::memset(&q, 0, sizeof(q));
 }
@@ -864,19 +865,17 @@ extern "C" int sem_ctx_set_ns_schur(sem_ctx* c, const sem_ns_schur_desc* d) {
     const MeshDev& g = c->g;
     const int n1 = g.P + 1, nexg = (g.NXg - 1) / g.P, ney = g.ney;
     const size_t vlen = (size_t)g.NX * g.LD;
-    // tables: wl[n1] wr[n1] | x: ta tinv tcp [nexg+1] each | y: ta tinv tcp [ney+1] each | lfx[NXg] | lfy[NY]
-    const size_t ntab = 2 * n1 + 3 * (nexg + 1) + 3 * (ney + 1) + g.NXg + g.NY;
+    // tables: wl[n1] wr[n1] | lfx[NXg] | lfy[NY]
+    const size_t ntab = 2 * n1 + g.NXg + g.NY;
     std::vector<double> h(ntab);
     size_t o = 0;
     auto put = [&](const double* src, size_t n) { size_t at = o; std::memcpy(h.data() + o, src, sizeof(double) * n); o += n; return at; };
     const size_t o_wl = put(d->wl, n1), o_wr = put(d->wr, n1);
-    const size_t o_xa = put(d->ta_x, nexg + 1), o_xi = put(d->tinv_x, nexg + 1), o_xc = put(d->tcp_x, nexg + 1);
-    const size_t o_ya = put(d->ta_y, ney + 1), o_yi = put(d->tinv_y, ney + 1), o_yc = put(d->tcp_y, ney + 1);
     const size_t o_lx = put(d->lfx, g.NXg), o_ly = put(d->lfy, g.NY);
     SEM_CUDA(cudaMalloc(&q.tables, sizeof(double) * ntab));
     SEM_CUDA(cudaMemcpy(q.tables, h.data(), sizeof(double) * ntab, cudaMemcpyHostToDevice));
-    q.px = PwDir{g.NXg, q.tables + o_wl, q.tables + o_wr, q.tables + o_xa, q.tables + o_xi, q.tables + o_xc};
-    q.py = PwDir{g.NY, q.tables + o_wl, q.tables + o_wr, q.tables + o_ya, q.tables + o_yi, q.tables + o_yc};
+    q.px = PwDir{g.NXg, q.tables + o_wl, q.tables + o_wr};
+    q.py = PwDir{g.NY, q.tables + o_wl, q.tables + o_wr};
     auto zalloc = [](double** p, size_t n) -> int {
         SEM_CUDA(cudaMalloc(p, sizeof(double) * n));
         SEM_CUDA(cudaMemset(*p, 0, sizeof(double) * n));
@@ -887,8 +886,20 @@ extern "C" int sem_ctx_set_ns_schur(sem_ctx* c, const sem_ns_schur_desc* d) {
     for (int k : {SW_Y, SW_Z1, SW_R1, SW_NR, SW_RHO, SW_E})
         if (zalloc(&q.w[k], vlen)) return -1;
     if (zalloc(&q.lc, vlen) || zalloc(&q.mc, vlen) || zalloc(&q.sums, 2)) return -1;
-    q.ldcy = round_up(ney + 1, 2);
-    if (zalloc(&q.cx, (size_t)(nexg + 1) * g.LD) || zalloc(&q.cy, (size_t)g.NX * q.ldcy)) return -1;
+    // projector coefficients c = W^T (M v) -> T^-1 c: the small dense inverse is applied by the DMMA GEMM (a Thomas sweep
+    // with one thread per line is a latency-bound chain: 9 % of an iteration at a million nodes in the round-2 launch list)
+    q.tile = fdm_tile_for(std::min(g.NXg, g.NY) - 2);
+    q.kxp = round_up(nexg + 1, q.tile);
+    q.kyp = round_up(ney + 1, q.tile);
+    q.ldx = round_up(g.NY, q.tile);
+    q.rowsy = round_up(g.NX, q.tile);
+    if (zalloc(&q.cx, (size_t)q.kxp * q.ldx) || zalloc(&q.cx2, (size_t)q.kxp * q.ldx) || zalloc(&q.cy, (size_t)q.rowsy * q.kyp) ||
+        zalloc(&q.cy2, (size_t)q.rowsy * q.kyp) || zalloc(&q.TinvX, (size_t)q.kxp * q.kxp) || zalloc(&q.TinvY, (size_t)q.kyp * q.kyp))
+        return -1;
+    SEM_CUDA(cudaMemcpy2D(q.TinvX, sizeof(double) * q.kxp, d->Tinv_x, sizeof(double) * (nexg + 1), sizeof(double) * (nexg + 1),
+                          nexg + 1, cudaMemcpyHostToDevice));
+    SEM_CUDA(cudaMemcpy2D(q.TinvY, sizeof(double) * q.kyp, d->Tinv_y, sizeof(double) * (ney + 1), sizeof(double) * (ney + 1), ney + 1,
+                          cudaMemcpyHostToDevice));
     const Regions rg{c->pin_gx, c->pin_iy};
     if (member_vectors(g, c->tab(), rg, q.tables + o_lx, q.tables + o_ly, q.lc, q.mc, 0)) return -1;
     SEM_CUDA(cudaDeviceSynchronize());
@@ -955,13 +966,18 @@ static int schur_add_ring(sem_ctx* c, double* z, const double* y, cudaStream_t s
 static int schur_project(sem_ctx* c, int transposed, const double* v, double* u, double* out, cudaStream_t st) {
     sem_ctx::NsSchur& q = c->sch;
     const MeshDev& g = c->g;
-    if (pw_restrict(g, c->tab(), q.px, 0, transposed, v, q.cx, g.LD, st)) return -1;
-    if (c->has_comm && comm_allreduce_sum(c->comm, q.cx, ((g.NXg - 1) / g.P + 1) * g.LD, st)) return -1;
-    if (pw_solve(g, q.px, 0, q.cx, g.LD, st)) return -1;
-    if (pw_prolong(g, c->tab(), q.px, 0, transposed, q.cx, g.LD, v, u, st)) return -1;          // u = (I - P_x) v
-    if (pw_restrict(g, c->tab(), q.py, 1, transposed, u, q.cy, q.ldcy, st)) return -1;
-    if (pw_solve(g, q.py, 1, q.cy, q.ldcy, st)) return -1;
-    if (pw_prolong(g, c->tab(), q.py, 1, transposed, q.cy, q.ldcy, u, u, st)) return -1;        // u = (I - P_y) u
+    GemmArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nprob = 1; a.batch = 1; a.tile = q.tile;
+    if (pw_restrict(g, c->tab(), q.px, 0, transposed, v, q.cx, q.ldx, st)) return -1;
+    if (c->has_comm && comm_allreduce_sum(c->comm, q.cx, q.kxp * q.ldx, st)) return -1;
+    a.p[0] = GemmProblem{q.TinvX, q.cx, q.cx2, q.kxp, q.ldx, q.ldx, 0, 0, 0, q.kxp, q.ldx, q.kxp, nullptr, nullptr};   // cx2 = T^-1 cx
+    if (gemm_launch(a, EPI_NONE, st)) return -1;
+    if (pw_prolong(g, c->tab(), q.px, 0, transposed, q.cx2, q.ldx, v, u, st)) return -1;        // u = (I - P_x) v
+    if (pw_restrict(g, c->tab(), q.py, 1, transposed, u, q.cy, q.kyp, st)) return -1;
+    a.p[0] = GemmProblem{q.cy, q.TinvY, q.cy2, q.kyp, q.kyp, q.kyp, 0, 0, 0, q.rowsy, q.kyp, q.kyp, nullptr, nullptr};  // cy2 = cy T^-1
+    if (gemm_launch(a, EPI_NONE, st)) return -1;
+    if (pw_prolong(g, c->tab(), q.py, 1, transposed, q.cy2, q.kyp, u, u, st)) return -1;        // u = (I - P_y) u
     return aux_sub(v, u, out, (long long)g.NX * g.LD, st);                                      // out = v - u
 }
 

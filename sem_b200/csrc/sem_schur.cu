@@ -237,30 +237,6 @@ int pw_restrict(const MeshDev& g, TabDev t, const PwDir& d, int dir, int transpo
     return 0;
 }
 
-// Thomas solve of T c' = c with precomputed factors, in place.  dir 0: thread per column iy, stride ldc between k;
-// dir 1: thread per line ix, consecutive k.
-__global__ void k_pw_solve(const PwDir d, int ne, int nthreads, long long tstride, long long kstride, double* __restrict__ c) {
-    const int tix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tix >= nthreads) return;
-    double* p = c + tix * tstride;
-    double prev = 0.0;
-    for (int k = 0; k <= ne; ++k) {
-        prev = (p[k * kstride] - d.ta[k] * prev) * d.tinv[k];
-        p[k * kstride] = prev;
-    }
-    for (int k = ne - 1; k >= 0; --k) {
-        prev = p[k * kstride] - d.tcp[k] * prev;
-        p[k * kstride] = prev;
-    }
-}
-int pw_solve(const MeshDev& g, const PwDir& d, int dir, double* c, int ldc, cudaStream_t st) {
-    const int ne = (d.n - 1) / g.P;
-    if (dir == 0) k_pw_solve<<<(g.NY + 127) / 128, 128, 0, st>>>(d, ne, g.NY, 1, ldc, c);
-    else k_pw_solve<<<(g.NX + 127) / 128, 128, 0, st>>>(d, ne, g.NX, ldc, 1, c);
-    SEM_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // out = v - W c' (transposed: v - M W c') on the interior nodes of the direction, out = v elsewhere.  One thread per node.
 __global__ void k_pw_prolong(const MeshDev g, const TabDev t, const PwDir d, int dir, int transposed, const double* __restrict__ c,
                              int ldc, const double* v, double* out) {

@@ -38,14 +38,12 @@ struct PwDir {
     int n;                 // GLOBAL nodes of the direction, ne = (n - 1) / P elements
     const double* wl;      // [P+1] device: (1 - xn_j) L_P(xi_j)  (value of the left-vertex function at local node j)
     const double* wr;      // [P+1] device: xn_j L_P(xi_j)
-    const double* ta;      // [ne+1] Thomas factors of the tridiagonal Gram matrix T = W^T M W: sub-diagonal
-    const double* tinv;    // [ne+1] 1 / (b_k - a_k c'_{k-1})
-    const double* tcp;     // [ne+1] c'_k
 };
-// c[k][iy] (dir 0, k = GLOBAL vertex index, ld = g.LD) or c[ix][k] (dir 1, ld = ldc): restriction W^T (M v) (transposed: W^T v)
+// c[k][iy] (dir 0, k = GLOBAL vertex index) or c[ix][k] (dir 1), pitch ldc: restriction W^T (M v) (transposed: W^T v); the
+// coefficients of the projection are T^-1 c with the (dense, small) inverse of the tridiagonal Gram matrix T = W^T M W,
+// applied by the DMMA GEMM (sem_capi.cu)
 int pw_restrict(const MeshDev& g, TabDev t, const PwDir& d, int dir, int transposed, const double* v, double* c, int ldc,
                 cudaStream_t st);
-int pw_solve(const MeshDev& g, const PwDir& d, int dir, double* c, int ldc, cudaStream_t st);
 // out = v - W c (transposed: v - M W c) on the interior nodes, out = v elsewhere (out may alias v)
 int pw_prolong(const MeshDev& g, TabDev t, const PwDir& d, int dir, int transposed, const double* c, int ldc, const double* v,
                double* out, cudaStream_t st);

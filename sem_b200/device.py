@@ -304,15 +304,7 @@ class SemDevice:
             W[0] = 0.0
             W[-1] = 0.0
             T = W.T @ (Mh[:, None] * W)
-            b, a = np.diag(T).copy(), np.append(0.0, np.diag(T, -1))
-            csup = np.append(np.diag(T, 1), 0.0)
-            tinv, tcp = np.zeros(nel + 1), np.zeros(nel + 1)
-            prev = 0.0
-            for k in range(nel + 1):
-                den = b[k] - a[k] * prev
-                tinv[k] = 1.0 / den if den != 0.0 else 0.0
-                prev = csup[k] * tinv[k]
-                tcp[k] = prev
+            Tinv = np.linalg.inv(T) if two_level else np.zeros_like(T)     # P = 1: no two-level stage (T is singular)
             if two_level:
                 # coarse pencil (E^T R(sigma) E, M_II), R(sigma) = G E (K_II + sigma M_II)^-1 E^T G^T, sigma = lambda_s / 4
                 st = torch.from_numpy(s).to(K.device)
@@ -323,7 +315,7 @@ class SemDevice:
             else:
                 R = K
             glf = (G.T @ torch.from_numpy(lf).to(G.device)).cpu().numpy()       # G1^T lf: enters the velocity part of the null vector
-            dirs.append(dict(K=K, M=M, R=R, n=n, lf=lf, a=a, tinv=tinv, tcp=tcp, Mh=Mh, glf=glf))
+            dirs.append(dict(K=K, M=M, R=R, n=n, lf=lf, Tinv=Tinv, Mh=Mh, glf=glf))
         X_, Y_ = dirs
         self._set_plan(1, X_["K"], X_["M"], (0, X_["n"]), Y_["K"], Y_["M"], (0, Y_["n"]), 0)
         if two_level:
@@ -335,7 +327,7 @@ class SemDevice:
         singular = bool(on_boundary < 1e-12 and abs(lcx[pin_ix] * lcy[pin_iy]) < 1e-12)
         den = float((X_["Mh"] * lcx * lcx).sum() * (Y_["Mh"] * lcy * lcy).sum())
         arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in
-                (wl, wr, X_["a"], X_["tinv"], X_["tcp"], Y_["a"], Y_["tinv"], Y_["tcp"], lcx, lcy)]
+                (wl, wr, X_["Tinv"], Y_["Tinv"], lcx, lcy)]
         from . import SEM
         cheb_lo, cheb_hi, cheb_steps = SEM.ring_chebyshev_parameters(P, self.N_ex, self.N_ey, self.dx, self.dy, int(pin))
         desc = L.sem_ns_schur_desc(*[v.ctypes.data for v in arrs], int(singular), int(two_level),
