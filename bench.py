@@ -11,6 +11,11 @@ public Python class with pinned HOST buffers (H2D of the input field and D2H of 
 For N > 1 the element columns are partitioned across the ranks (strong scaling of the fixed config-5 mesh) with an
 NCCL exchange of the interface node lines.
 
+Secondary numbers of the same run go to `extra` (BASELINE.json metric part ii and configs 1-4): a steady Navier-Stokes solve
+of a 19.7M-DOF lid-driven cavity partitioned over the N ranks (`extra.ns_solve`, every N), the NS / CD / Boussinesq examples
+at their own sizes with the reference's algorithm timed on the host IN THE SAME RUN (N = 1), a weak-scaling apply, and -- for
+N > 1 -- a parity field: the partitioned applies against the same applies on one GPU.
+
 `--impl reference` times the reference's own CPU implementation of this apply -- scipy CSR mat-vec on the host, on
 matrices value-identical to the reference's (oracle port, the reference itself cannot build this mesh: SURVEY 8c) --
 on a bounded sample mesh.
@@ -230,12 +235,29 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     assert np.isfinite(res_host).all()
+    # the same call with an ordinary (pageable) numpy input, what OpenMDAO hands the solvers (views into its root vectors)
+    pageable_in = np.random.default_rng(rank + 100).standard_normal(n_local)
+    cd._get_dresiduals(pageable_in)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res_host = cd._get_dresiduals(pageable_in)
+    sync_all()
+    e2e_pageable_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_pageable_s], device=d.tdev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_pageable_s = float(t.item())
+    del res_host, pageable_in, host_in
+
+    parity = partition_parity(sem_b200, rank, world, local) if world > 1 else None
 
     # ---- N > 1: a steady CD solve of the whole config-5 mesh (67.1 M nodes), partitioned, distributed FDM preconditioner ------
     part_solve = None
     if world > 1 and not args.no_extra:
         try:
             del dT, out
+            torch.cuda.empty_cache()
             cd._mtol, cd._restart = 1e-8, 100
             xs, ys = cd.points[0], cd.points[1]
             ub, vb = ys - 0.5, 0.5 - xs
@@ -251,6 +273,13 @@ def run_ours(args):
         except Exception as exc:                         # a solver failure must not lose the headline line
             part_solve = {"error": str(exc)[:200]}
 
+    shared_extra = {}
+    if not args.no_extra:
+        del cd
+        torch.cuda.empty_cache()
+        shared_extra["ns_solve"] = ns_solve_large(sem_b200, rank, world, local, sync_all)
+        shared_extra["weak_scaling_apply"] = weak_scaling_apply(sem_b200, rank, world, local, sync_all, steps)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -258,9 +287,9 @@ def run_ours(args):
 
     peak, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_NODE * n_local / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    traffic = None                                   # per launch of THIS line: known from the ncu capture of the whole mesh only
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if world == 1 and os.path.exists(prof):
         with open(prof) as f:
             traffic = json.load(f).get("cd_jvp_dram_bytes_per_launch")
     line = {
@@ -276,12 +305,18 @@ def run_ours(args):
                      "algorithmic_bytes_per_node": ALG_BYTES_PER_NODE, "nodes_per_launch": n_local},
         "e2e": {"value": n_global / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 8),
                 "d2h_bytes_per_step": int(n_local * 8), "ms_per_step": e2e_s * 1e3,
-                "api": "ConvectionDiffusionSolver._get_dresiduals(numpy pinned) -> numpy"},
+                "api": "ConvectionDiffusionSolver._get_dresiduals(numpy pinned) -> numpy",
+                "pageable_input": {"value": n_global / e2e_pageable_s / 1e9, "ms_per_step": e2e_pageable_s * 1e3,
+                                   "note": "same call with an ordinary numpy array (what OpenMDAO passes); result still lands "
+                                           "in a recycled page-locked block"}},
         "gpu_launches": steps,
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
+    line["extra"] = dict(shared_extra)
     if part_solve is not None:
-        line["extra"] = {"cd_solve_config5_partitioned": part_solve}
+        line["extra"]["cd_solve_config5_partitioned"] = part_solve
     if world == 1:
         cval, cdt, cn = cpu_apply_sample(20, 3)
         line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": 1,
@@ -289,21 +324,148 @@ def run_ours(args):
                                 "sample": f"{CPU_SAMPLE_NE}x{CPU_SAMPLE_NE} elements, P={P_ORDER} ({cn} nodes), scipy CSR "
                                           f"mat-vec of the reference-identical Sys matrix, 20 applies, {cdt * 1e3:.1f} ms each"}
         if not args.no_extra:
-            line["extra"] = extra_numbers(sem_b200, d, lib, cd, st)
+            line["extra"].update(extra_numbers(sem_b200, local))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def extra_numbers(sem_b200, d, lib, cd, st):
-    """Secondary numbers of the same run (not the headline): the other fused applies and one steady NS solve."""
+NS_BIG_NE = 320           # extra.ns_solve: 320 x 320 elements, P = 8 -> 2561^2 nodes/field, 19.7M DOF (north star: >= 16M DOF)
+
+
+def ns_solve_large(sem_b200, rank, world, local, sync_all):
+    """Steady incompressible NS (NS example physics: lid-driven cavity, Re = 400, T = 0; reference defaults mtol = 1e-7,
+    mtol_newton = 1e-5) on NS_BIG_NE^2 elements of order 8, element columns partitioned over the ranks: distributed
+    fast-diagonalisation plans, two-level Schur preconditioner, NVLink interface exchange, all-reduced Krylov dots."""
+    import numpy as np
+    import torch
+    try:
+        ne = NS_BIG_NE
+        t0 = time.perf_counter()
+        ns = sem_b200.NavierStokesSolver(1.0, 1.0, 400.0, 0.0, P_ORDER, ne, ne, u_N=1.0, iprint=[], device=local, restart=600,
+                                         **({"partition": (rank, world)} if world > 1 else {}))
+        T = np.zeros(ns._dev.N_local)
+        ns._krylov()                                      # plans, Schur tables (one-off set-up, reported separately)
+        sync_all()
+        t1 = time.perf_counter()
+        u, v, p = ns._get_solution(T)
+        sync_all()
+        t2 = time.perf_counter()
+        d = ns._dev
+        res = d.zeros(3)
+        st3 = d.zeros(3)
+        for k, a in enumerate((u, v, p)):
+            d.to_device(a, st3[k])
+        ns._residual_dev(st3[0], st3[1], st3[2], d.to_device(T, ns._in[3]), res)
+        rn = ns._spectral_norm(res)
+        out = {"wall_s": t2 - t1, "setup_s": t1 - t0, "newton_its": ns._k, "krylov_its": list(ns.krylov_iters),
+               "nodes_per_field": ns.N, "dof": 3 * ns.N, "mesh": f"{ne}x{ne} elements, P={P_ORDER}", "Re": 400.0,
+               "newton_residual": rn, "newton_limit": ns._mtol_newton * float(np.sqrt(3 * ns.N)),
+               "converged": bool(rn <= ns._mtol_newton * np.sqrt(3 * ns.N)), "precond": "full (two-level Schur + PCD)",
+               "peak_mem_gb_rank0": torch.cuda.max_memory_allocated() / 2 ** 30, "n_gpus": world,
+               "tolerances": "reference defaults (mtol 1e-7, mtol_newton 1e-5)"}
+        del ns, res, st3
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:                              # a solver failure must not lose the headline line
+        return {"error": str(exc)[:300]}
+
+
+def weak_scaling_apply(sem_b200, rank, world, local, sync_all, steps):
+    """Weak scaling of the headline apply: config 5 PER GPU (global mesh 1024 N x 1024 elements, one 1024-column slab per rank)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from sem_b200 import _lib as L
+    try:
+        cd = sem_b200.ConvectionDiffusionSolver(float(world), 1.0, PE, P_ORDER, NE * world, NE, T_W=0.5, T_E=-0.5, device=local,
+                                                **({"partition": (rank, world)} if world > 1 else {}))
+        d = cd._dev
+        gen = torch.Generator(device=d.tdev).manual_seed(rank)
+        x, y = d.zeros(), d.zeros()
+        for t in (x, cd._u, cd._v):
+            t[:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
+        cd._have_sys = True
+        st = cd._state(with_jac=False)
+        step = lambda: L.check(d.lib.sem_cd_jvp(d.ctx, C.byref(st), x.data_ptr(), None, None, y.data_ptr(), d.stream), "sem_cd_jvp")
+        for _ in range(5):
+            step()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=d.tdev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        n_global = (NE * world * P_ORDER + 1) * (NE * P_ORDER + 1)
+        out = {"gdof_s": n_global / ms / 1e6, "ms_per_step": ms, "nodes": n_global,
+               "mesh": f"{NE * world}x{NE} elements, P={P_ORDER}: config 5 per GPU"}
+        del cd, x, y
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:
+        return {"error": str(exc)[:300]}
+
+
+def partition_parity(sem_b200, rank, world, local):
+    """Correctness carried on every N > 1 line: the partitioned fused applies (CD Jacobian, 3-field NS Jacobian) on a mid-size mesh
+    against the SAME applies on one GPU (each rank also holds the whole mesh; the one-GPU path is gated against the reference's
+    golden vectors and the CPU restatement by tests/), relative L2 error of the slab, maximum over ranks.  Bar: 1e-12."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sem_b200.partition import Partition
+    try:
+        P, nx, ny = P_ORDER, 32 * world, 96
+        kw = dict(L_x=1.0, L_y=1.0, P=P, N_ex=nx, N_ey=ny)
+        part = Partition(nx, ny, P, rank, world)
+        sl = part.local_slice
+        rng = np.random.default_rng(7)
+        N = (nx * P + 1) * (ny * P + 1)
+        T, u, v, p, a, b, c = (rng.standard_normal(N) for _ in range(7))
+        errs = {}
+        rel = lambda x, y: float(np.linalg.norm(x - y) / np.linalg.norm(y))
+        cd1 = sem_b200.ConvectionDiffusionSolver(Pe=PE, T_W=0.5, T_E=-0.5, device=local, **kw)
+        cdp = sem_b200.ConvectionDiffusionSolver(Pe=PE, T_W=0.5, T_E=-0.5, device=local, partition=(rank, world), **kw)
+        cd1._get_residuals(T, u, v)
+        cdp._get_residuals(sl(T), sl(u), sl(v))
+        errs["cd_jvp"] = rel(cdp._get_dresiduals(sl(a)), sl(cd1._get_dresiduals(a)))
+        ns1 = sem_b200.NavierStokesSolver(Re=400.0, Gr=10.0, u_N=1.0, iprint=[], device=local, **kw)
+        nsp = sem_b200.NavierStokesSolver(Re=400.0, Gr=10.0, u_N=1.0, iprint=[], device=local, partition=(rank, world), **kw)
+        r1 = ns1._get_residuals(u, v, p, T)
+        rp = nsp._get_residuals(sl(u), sl(v), sl(p), sl(T))
+        errs["ns_residual"] = max(rel(x, sl(y)) for x, y in zip(rp, r1))
+        ns1._calc_jacobians(u, v)
+        nsp._calc_jacobians(sl(u), sl(v))
+        j1 = ns1._get_dresiduals(a, b, c)
+        jp = nsp._get_dresiduals(sl(a), sl(b), sl(c))
+        errs["ns_jvp"] = max(rel(x, sl(y)) for x, y in zip(jp, j1))
+        t = torch.tensor([errs[k] for k in sorted(errs)], device=torch.device("cuda", local), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        errs = {k: float(t[i]) for i, k in enumerate(sorted(errs))}
+        del cd1, cdp, ns1, nsp
+        torch.cuda.empty_cache()
+        return {"mesh": f"{nx}x{ny} elements, P={P} ({N} nodes)", "against": "the same applies on one GPU", "max_rel_err": errs,
+                "bar": 1e-12, "ok": bool(max(errs.values()) <= 1e-12)}
+    except Exception as exc:
+        return {"error": str(exc)[:300]}
+
+
+def extra_numbers(sem_b200, local):
+    """Secondary numbers of the N = 1 run (not the headline): the other fused applies, the reference's examples (BASELINE
+    configs 1-4) with the reference's own algorithm timed on the host in this run, and a large CD solve."""
     import ctypes as C
     import numpy as np
     import torch
     from sem_b200 import _lib as L
+    from sem_b200 import Boussinesq_SequentialCoupler as bsc
     out = {}
     peak, _ = measured_peaks()
-    n = d.NX * d.NY
 
     def timeit(fn, k=10):
         for _ in range(3):
@@ -317,51 +479,119 @@ def extra_numbers(sem_b200, d, lib, cd, st):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / k
 
-    x, y = cd._buf[0], cd._buf[1]
-    t = timeit(lambda: d.apply_stiffness(x, y))
-    out["stiffness_apply"] = {"gdof_s": n / t / 1e6, "hbm_frac": 16 * n / t / 1e6 / peak, "ms": t, "bytes_per_node": 16}
-    del cd
-    torch.cuda.empty_cache()
-    ns = sem_b200.NavierStokesSolver(1.0, 1.0, 400.0, 0.0, P_ORDER, NE, NE, u_N=1.0, iprint=[], device=d.device)
-    gen = torch.Generator(device=d.tdev).manual_seed(1)
-    for k in range(3):
-        ns._in[k][:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
-    ns._uv.copy_(ns._in[:2])
-    ns._have_sys = True
-    ns._jacobians_dev(ns._in[0], ns._in[1])
-    nst = ns._state()
-    nd = ns._dev
-    t = timeit(lambda: L.check(lib.sem_ns_jvp(nd.ctx, C.byref(nst), ns._in[0].data_ptr(), ns._in[1].data_ptr(),
-                                              ns._in[2].data_ptr(), None, ns._out[0].data_ptr(), ns._out[1].data_ptr(),
-                                              ns._out[2].data_ptr(), nd.stream), "sem_ns_jvp"), k=5)
-    out["ns_jvp_apply"] = {"gdof_s": 3 * n / t / 1e6, "hbm_frac": 96 * n / t / 1e6 / peak, "ms": t, "bytes_per_node": 96}
-    del ns
-    torch.cuda.empty_cache()
-    # steady NS solve, BASELINE config 2 (Examples/NavierStokes_Example.py: P=4, 16x16, Re=400, lid u_N=1), default tolerances
-    ns2 = sem_b200.NavierStokesSolver(1, 1, 400, 0, 4, 16, 16, u_N=1, iprint=[], device=d.device)
-    T0 = np.zeros(ns2.N)
-    ns2._get_solution(T0)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    ns2._get_solution(T0)
-    torch.cuda.synchronize()
-    out["ns_solve_config2"] = {"wall_s": time.perf_counter() - t0, "newton_its": ns2._k,
-                               "krylov_its": ns2.krylov_iters[-ns2._k:], "tolerances": "reference defaults (1e-7 / 1e-5)",
-                               "reference_cpu_wall_s_probe": 21.9, "reference_probe_source": "BASELINE.md section 2"}
-    del ns2
-    # a large steady CD solve (512 x 512 elements, P = 8: 16.8 M nodes) with the fast-diagonalisation preconditioner
-    cdb = sem_b200.ConvectionDiffusionSolver(1, 1, PE, P_ORDER, 512, 512, T_W=0.5, T_E=-0.5, mtol=1e-10, restart=60,
-                                             device=d.device)
-    ub = cdb._get_vector(lambda x, y: y - 0.5)
-    vb = cdb._get_vector(lambda x, y: 0.5 - x)
-    cdb._get_solution(ub, vb)                  # includes the one-off eigen-decompositions
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    Tb = cdb._get_solution(ub, vb)
-    torch.cuda.synchronize()
-    out["cd_solve_16M_nodes"] = {"wall_s": time.perf_counter() - t0, "krylov_its": cdb.last_iters, "nodes": cdb.N,
-                                 "resnorm": cdb.last_resnorm, "atol": 1e-10 * float(np.sqrt(cdb.N)),
-                                 "note": "host vectors in / out included; preconditioner fast diagonalisation"}
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as exc:
+            out[name] = {"error": str(exc)[:300]}
+        torch.cuda.empty_cache()
+
+    def applies():
+        d = sem_b200.SemDevice(P_ORDER, NE, NE, 1.0 / NE, 1.0 / NE, device=local)
+        n = d.NX * d.NY
+        gen = torch.Generator(device=d.tdev).manual_seed(1)
+        x, y = d.zeros(), d.zeros()
+        x[:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64)
+        t = timeit(lambda: d.apply_stiffness(x, y))
+        out["stiffness_apply"] = {"gdof_s": n / t / 1e6, "hbm_frac": 16 * n / t / 1e6 / peak, "ms": t, "bytes_per_node": 16}
+        del d, x, y
+        torch.cuda.empty_cache()
+        ns = sem_b200.NavierStokesSolver(1.0, 1.0, 400.0, 0.0, P_ORDER, NE, NE, u_N=1.0, iprint=[], device=local)
+        nd = ns._dev
+        for k in range(3):
+            ns._in[k][:, :nd.NY] = torch.randn((nd.NX, nd.NY), generator=gen, device=nd.tdev, dtype=torch.float64)
+        ns._uv.copy_(ns._in[:2])
+        ns._have_sys = True
+        ns._jacobians_dev(ns._in[0], ns._in[1])
+        nst = ns._state()
+        t = timeit(lambda: L.check(nd.lib.sem_ns_jvp(nd.ctx, C.byref(nst), ns._in[0].data_ptr(), ns._in[1].data_ptr(),
+                                                     ns._in[2].data_ptr(), None, ns._out[0].data_ptr(), ns._out[1].data_ptr(),
+                                                     ns._out[2].data_ptr(), nd.stream), "sem_ns_jvp"), k=5)
+        return {"gdof_s": 3 * n / t / 1e6, "hbm_frac": 96 * n / t / 1e6 / peak, "ms": t, "bytes_per_node": 96}
+
+    guarded("ns_jvp_apply", applies)
+
+    def cd_config1():
+        """BASELINE config 1: Examples/ConvectionDiffusion_Example.py (P=4, 16x16, Pe=40, u = y - 1/2, v = 1/2 - x)."""
+        kw = dict(L_x=1.0, L_y=1.0, Pe=40.0, P=4, N_ex=16, N_ey=16, T_W=0.5, T_E=-0.5)
+        cd = sem_b200.ConvectionDiffusionSolver(device=local, **kw)
+        u = cd._get_vector(lambda x, y: y - 0.5)
+        v = cd._get_vector(lambda x, y: 0.5 - x)
+        cd._get_solution(u, v)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        Tg = cd._get_solution(u, v)
+        torch.cuda.synchronize()
+        tg = time.perf_counter() - t0
+        from oracle import sem_oracle as so               # host leg: the reference's algorithm, timed in this run
+        cdo = so.CDOracle(**kw)
+        t0 = time.perf_counter()
+        Th, evals = cdo._get_solution_lgmres(u, v)
+        th = time.perf_counter() - t0
+        return {"wall_s": tg, "krylov_its": cd.last_iters, "host_wall_s": th, "host_operator_evals": evals,
+                "host_kind": "port of CD:123-156 (SciPy LGMRES, no preconditioner, inner_m = 0.3 N) on this box, 1 core",
+                "rel_diff_vs_host": float(np.linalg.norm(Tg - Th) / np.linalg.norm(Th))}
+
+    guarded("cd_solve_config1", cd_config1)
+
+    def ns_config2():
+        """BASELINE config 2: Examples/NavierStokes_Example.py (P=4, 16x16, Re=400, lid u_N=1), reference default tolerances."""
+        res = {"tolerances": "reference defaults (mtol 1e-7, mtol_newton 1e-5)"}
+        T0 = np.zeros(4225)
+        for precond in ("auto", "full"):
+            ns2 = sem_b200.NavierStokesSolver(1, 1, 400, 0, 4, 16, 16, u_N=1, iprint=[], device=local, precond=precond)
+            ns2._get_solution(T0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ug, vg, pg = ns2._get_solution(T0)
+            torch.cuda.synchronize()
+            res[precond] = {"wall_s": time.perf_counter() - t0, "newton_its": ns2._k, "krylov_its": ns2.krylov_iters[-ns2._k:],
+                            "total_krylov": int(sum(ns2.krylov_iters[-ns2._k:]))}
+            del ns2
+        res["wall_s"] = res["auto"]["wall_s"]
+        from oracle import sem_oracle as so               # host leg: the reference's algorithm, timed in this run
+        nso = so.NSOracle(1, 1, 400, 0, 4, 16, 16, u_N=1)
+        t0 = time.perf_counter()
+        uh, vh, ph = nso._get_solution(T0, algorithm='reference')
+        res["host_wall_s"] = time.perf_counter() - t0
+        res["host_newton_its"], res["host_schur_matvecs"] = nso._k, nso.schur_matvecs
+        res["host_kind"] = "port of NS:162-270 (SuperLU velocity block + SciPy LGMRES on the Schur complement) on this box, 1 core"
+        res["rel_diff_vs_host"] = {"u": float(np.linalg.norm(ug - uh) / np.linalg.norm(uh)),
+                                   "p": float(np.linalg.norm(pg - ph) / np.linalg.norm(ph)),
+                                   "note": "both stop at the reference's loose default tolerances"}
+        return res
+
+    guarded("ns_solve_config2", ns_config2)
+
+    def boussinesq(ne, mode, tol):
+        def f():
+            t0 = time.perf_counter()
+            title, T_e, u_e, v_e, iters = bsc.run_study(save=False, P=4, N_e=ne, mode=mode, mtol_nonlin=tol, mtol_gmres=1e-13 if
+                                                        mode == 'JNK' else 1e-10, mtol_internal=1e-13)
+            torch.cuda.synchronize()
+            return {"wall_s": time.perf_counter() - t0, "mode": mode, "mesh": f"NS {ne}x{ne}, CD {ne // 2}x{ne // 2}, P=4",
+                    "dof": 3 * (4 * ne + 1) ** 2 + (2 * ne + 1) ** 2, "iters_cd_ns_nonlin": [int(i) for i in iters],
+                    "umax_RePr": float(u_e.max() * 1e3 * 0.71), "mtol_nonlin": tol,
+                    "note": "study/Boussinesq_run.py physics (Re=1e3, Ra=1e3, Pr=0.71); set-up included"}
+        return f
+
+    guarded("boussinesq_config3", boussinesq(8, 'JNK', 1e-10))       # Examples/Boussinesq_Sequential_Example.py size
+    guarded("boussinesq_config4_1M_dof", boussinesq(128, 'GS', 1e-8))  # study run scaled to ~1 M DOF (BASELINE config 4)
+
+    def cd_16m():
+        cdb = sem_b200.ConvectionDiffusionSolver(1, 1, PE, P_ORDER, 512, 512, T_W=0.5, T_E=-0.5, mtol=1e-10, restart=60, device=local)
+        ub = cdb._get_vector(lambda x, y: y - 0.5)
+        vb = cdb._get_vector(lambda x, y: 0.5 - x)
+        cdb._get_solution(ub, vb)                  # includes the one-off eigen-decompositions
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cdb._get_solution(ub, vb)
+        torch.cuda.synchronize()
+        return {"wall_s": time.perf_counter() - t0, "krylov_its": cdb.last_iters, "nodes": cdb.N, "resnorm": cdb.last_resnorm,
+                "atol": 1e-10 * float(np.sqrt(cdb.N)),
+                "note": "host vectors in / out included; preconditioner: fast diagonalisation on the hand-written DMMA GEMM"}
+
+    guarded("cd_solve_16M_nodes", cd_16m)
     return out
 
 

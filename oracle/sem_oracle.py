@@ -287,6 +287,24 @@ class CDOracle:
         res = self._get_residuals(T, u, v)
         return T + self._get_update(-res)
 
+    def _get_solution_lgmres(self, u, v, T0=None):
+        """The reference's OWN algorithm for the CD solve, restated (CD:123-170): matrix-free operator through
+        ``_get_dresiduals``, SciPy LGMRES without preconditioner, ``inner_m = int(0.3 N)``, ``atol = mtol sqrt(N)``.  Host timing
+        baseline of bench.py (`kind: port`).  Returns (T, operator evaluations)."""
+        T = np.zeros(self.N) if T0 is None else T0
+        res = self._get_residuals(T, u, v)
+        count = [0]
+
+        def mv(x):
+            count[0] += 1
+            return self._get_dresiduals(x)
+
+        A = spla.LinearOperator((self.N, self.N), mv, dtype=float)
+        dT, info = spla.lgmres(A, -res, atol=self._mtol * np.sqrt(self.N), rtol=0, inner_m=int(self.N * 0.3))
+        if info != 0:
+            raise RuntimeError(f'ConvectionDiffusion LGMRES: Failed to converge in {info} iterations')
+        return T + dT, count[0]
+
     def _get_vector(self, f_func):
         return f_func(self.points[0], self.points[1])
 
@@ -465,8 +483,53 @@ class NSOracle:
         alpha = (m @ (x1 - x0)) / (m @ q)
         return tuple(np.split(x1 - alpha * q, 3))
 
-    def _get_solution(self, T, u0=None, v0=None, p0=None, max_newton=50):
-        """Newton loop, stop on the spectral norm of the 3 x N residual array <= mtol_newton sqrt(3N)  (NS:238-270)."""
+    def _get_update_schur(self, dres_u, dres_v, dres_cont, du0=None, dv0=None, dp0=None):
+        """The reference's OWN algorithm for the linearised system, restated line by line (NS:162-236): SuperLU of the
+        boundary-modified 2N x 2N velocity Jacobian (NS:178-184), right-hand side and matrix-free operator of the pressure Schur
+        complement through ``_get_dresiduals`` (NS:196-205), diagonal-mass preconditioner with the pin row passed through
+        (NS:208-212), SciPy LGMRES with ``inner_m = int(0.3 N)`` and ``atol = mtol sqrt(N)`` (NS:222-224), back-substitution
+        of the velocities (NS:233-234).  Used as the host timing baseline of bench.py (`kind: port`) and to cross-check
+        ``_get_update``; ``self.schur_matvecs`` counts the Schur operator evaluations."""
+        N = self.N
+        Sys = self._K + self._Re * (sps.diags(self._u) @ self._G_x + sps.diags(self._v) @ self._G_y)
+        Jac = sps.bmat([[Sys + sps.diags(self._gxu), sps.diags(self._gyu)],
+                        [sps.diags(self._gxv), Sys + sps.diags(self._gyv)]], format='lil')
+        mask = np.hstack((self._mask_bound,) * 2)
+        Jac[mask, :] = 0
+        Jac[mask, mask] = 1
+        lu = spla.splu(Jac.tocsc())
+        zero = np.zeros(N)
+
+        def solve_velo(ru, rv):
+            return np.split(lu.solve(np.hstack((ru, rv))), 2)
+
+        b_schur = dres_cont - self._get_dresiduals(*solve_velo(dres_u, dres_v), zero)[2]
+        count = [0]
+
+        def schur_mv(dp):
+            count[0] += 1
+            f_x, f_y = solve_velo(*self._get_dresiduals(zero, zero, dp)[:2])
+            return self._get_dresiduals(-f_x, -f_y, dp)[2]
+
+        def precon_mv(c):
+            z = c / self._M
+            z[self._pin] = c[self._pin]
+            return z
+
+        A = spla.LinearOperator((N, N), schur_mv, dtype=float)
+        M = spla.LinearOperator((N, N), precon_mv, dtype=float)
+        dp, info = spla.lgmres(A, b_schur, M=M, x0=dp0, atol=self._mtol * np.sqrt(N), rtol=0, inner_m=int(N * 0.3))
+        self.schur_matvecs = getattr(self, "schur_matvecs", 0) + count[0]
+        if info != 0:
+            raise RuntimeError(f'NavierStokes LGMRES: Failed to converge in {info} iterations')
+        b_u, b_v = self._get_dresiduals(zero, zero, dp)[:2]
+        du, dv = solve_velo(dres_u - b_u, dres_v - b_v)
+        return du, dv, dp
+
+    def _get_solution(self, T, u0=None, v0=None, p0=None, max_newton=50, algorithm='direct'):
+        """Newton loop, stop on the spectral norm of the 3 x N residual array <= mtol_newton sqrt(3N)  (NS:238-270).
+        algorithm: 'direct' (sparse LU of the 3-field Jacobian + member selection, ``_get_update``) or 'reference' (the
+        reference's Schur-complement LGMRES, ``_get_update_schur``)."""
         u = u0 if u0 is not None else np.zeros(self.N)
         v = v0 if v0 is not None else np.zeros(self.N)
         p = p0 if p0 is not None else np.zeros(self.N)
@@ -477,7 +540,8 @@ class NSOracle:
             if norm <= self._mtol_newton * np.sqrt(self.N * 3) or self._k >= max_newton:
                 break
             self._calc_jacobians(u, v)
-            du, dv, dp = self._get_update(-res_u, -res_v, -res_c)
+            solve = self._get_update_schur if algorithm == 'reference' else self._get_update
+            du, dv, dp = solve(-res_u, -res_v, -res_c)
             u += du
             v += dv
             p += dp
