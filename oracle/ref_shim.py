@@ -69,6 +69,18 @@ def install():
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+    # The reference's ``Solvers`` directory has no __init__.py (a namespace package), so the repository's own ``Solvers/`` shim
+    # package (a regular package) would win the import no matter the order of sys.path: bind the name to the reference's
+    # directory explicitly before anything is imported from it.
+    import os
+    pkg = sys.modules.get("Solvers")
+    ref_dir = os.path.join(REFERENCE_ROOT, "Solvers")
+    if pkg is None or list(getattr(pkg, "__path__", [])) != [ref_dir]:
+        for name in [m for m in sys.modules if m == "Solvers" or m.startswith("Solvers.")]:
+            del sys.modules[name]
+        pkg = types.ModuleType("Solvers")
+        pkg.__path__ = [ref_dir]
+        sys.modules["Solvers"] = pkg
     from Solvers import GLL, SEM
     from Solvers.ConvectionDiffusion_Solver import ConvectionDiffusionSolver
     from Solvers.NavierStokes_Solver import NavierStokesSolver

@@ -192,6 +192,59 @@ def global_operators(P, N_ex, N_ey, dx, dy):
     return M, K, G_x, G_y
 
 
+class KronOps:
+    """The reference's global operators on meshes it cannot assemble (BASELINE config 5: 67 M nodes), through the Kronecker
+    identities of ``global_operators`` -- ``K = Kx (x) My + Mx (x) Ky``, ``G_x = Gx1 (x) My``, ``G_y = Mx (x) Gy1`` (value
+    identical to SEM.py:170-223, checked in tests/test_oracle.py) -- applied to a field stored as the 2-D array X[ix, iy]:
+    ``kron(A, B) vec(X) = vec(A X B^T)``.  Only sparse 1-D matrices and dense 2-D fields: seconds at 67 M nodes."""
+
+    def __init__(self, P, N_ex, N_ey, dx, dy):
+        Ms, Ks, Gs = mass_1d(P), stiff_1d(P), grad_1d(P)
+        self.Mx = _assembled_1d(dx / 2 * Ms, N_ex).diagonal()
+        self.My = _assembled_1d(dy / 2 * Ms, N_ey).diagonal()
+        self.Kx = _assembled_1d(2 / dx * Ks, N_ex)
+        self.Ky = _assembled_1d(2 / dy * Ks, N_ey)
+        self.Gx1 = _assembled_1d(Gs, N_ex)
+        self.Gy1 = _assembled_1d(Gs, N_ey)
+        self.shape = (N_ex * P + 1, N_ey * P + 1)
+
+    def K(self, X):
+        return (self.Kx @ X) * self.My[None, :] + self.Mx[:, None] * (self.Ky @ X.T).T
+
+    def Gx(self, X):
+        return (self.Gx1 @ X) * self.My[None, :]
+
+    def Gy(self, X):
+        return self.Mx[:, None] * (self.Gy1 @ X.T).T
+
+    def M(self, X):
+        return self.Mx[:, None] * X * self.My[None, :]
+
+    def cd_jvp(self, Pe, dT, u, v, dirichlet_wesn):
+        """CD:104-121 without the du/dv terms: Sys dT with Dirichlet rows = dT."""
+        Y = self.K(dT) + Pe * (u * self.Gx(dT) + v * self.Gy(dT))
+        W, E, S, N = dirichlet_wesn
+        if W: Y[0, :] = dT[0, :]
+        if E: Y[-1, :] = dT[-1, :]
+        if S: Y[:, 0] = dT[:, 0]
+        if N: Y[:, -1] = dT[:, -1]
+        return Y
+
+    def ns_jvp(self, Re, u, v, du, dv, dp):
+        """NS:138-160 (dT = None) about the state (u, v): Jacobian diagonals Re G u etc. (NS:123-136), velocity Dirichlet rows,
+        pressure-Neumann rows K[mask,:] dp, then the pin at node int(N/2)."""
+        sys_ = lambda X: self.K(X) + Re * (u * self.Gx(X) + v * self.Gy(X))
+        ru = sys_(du) + Re * self.Gx(u) * du + Re * self.Gy(u) * dv + self.Gx(dp)
+        rv = Re * self.Gx(v) * du + sys_(dv) + Re * self.Gy(v) * dv + self.Gy(dp)
+        rc = self.Gx(du) + self.Gy(dv)
+        Kp = self.K(dp)
+        for sl_ in ((0, slice(None)), (-1, slice(None)), (slice(None), 0), (slice(None), -1)):
+            ru[sl_], rv[sl_], rc[sl_] = du[sl_], dv[sl_], Kp[sl_]
+        pin = (self.shape[0] * self.shape[1]) // 2
+        rc[divmod(pin, self.shape[1])] = dp[divmod(pin, self.shape[1])]
+        return ru, rv, rc
+
+
 def x2xi(x, h):
     """Physical coordinate -> (element, xi)  (``SEM.py:23-36``): left-element convention at shared nodes."""
     frac, e = np.modf(np.asarray(x, dtype=np.float64) / h)

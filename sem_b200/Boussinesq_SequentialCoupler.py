@@ -171,16 +171,23 @@ def solve(cd: ConvectionDiffusionSolver, ns: NavierStokesSolver, mode='JNK', mto
                 dx = sys_.block_jacobi(-r)                         # LinearBlockJac, maxiter=1 (BSC:89)
                 # Armijo-Goldstein backtracking on the residual norm (om.ArmijoGoldsteinLS(rho=AGr, c=AGc, maxiter=AGi))
                 alpha, slope = 1.0, -rn
+                best = None
                 for _ in range(AGi + 1):
                     xt = x + alpha * dx
                     rt = sys_.residual(xt)
-                    if np.linalg.norm(rt) <= rn + AGc * alpha * slope:
+                    rtn = np.linalg.norm(rt)
+                    if best is None or rtn < best[2]:
+                        best = (xt, rt, rtn)
+                    if rtn <= rn + AGc * alpha * slope:
                         break
                     alpha *= AGr
-                x, r, rn = xt, rt, np.linalg.norm(rt)
+                else:
+                    xt, rt, rtn = best                             # no trial met the Armijo condition: keep the best one
+                x, r, rn = xt, rt, rtn
             info['nonlinear_its'] = it + 1
         else:
-            raise RuntimeError('Boussinesq Newton: Failed to converge')
+            if rn > atol_nonlin:                                   # the last allowed update may have converged
+                raise RuntimeError('Boussinesq Newton: Failed to converge')
     else:
         raise ValueError('Unknown method')                         # BSC:96
     info['iter_cd'], info['iter_ns'] = sys_.iter_cd, sys_.iter_ns

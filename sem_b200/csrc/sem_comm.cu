@@ -97,7 +97,9 @@ static int p2p_init(Comm& c, int NY) {
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
     if (ok && cudaMalloc(&c.box, bytes) != cudaSuccess) { cudaGetLastError(); c.box = nullptr; ok = 0; }
-    if (ok) SEM_CUDA(cudaMemset(c.box, 0, bytes));
+    // a LOCAL failure must not return before the collectives below (the other ranks would block in them): it only clears `ok`,
+    // and the agreement all-reduce then sends every rank to the NCCL fallback together
+    if (ok && cudaMemset(c.box, 0, bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     if (ok && cudaIpcGetMemHandle(&mine, c.box) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     // handles of all ranks (64 bytes each) + one double per rank for the agreement
     unsigned char* dh = nullptr;
@@ -132,6 +134,7 @@ static int p2p_init(Comm& c, int NY) {
     if (!c.p2p) {
         for (int s = 0; s < 2; ++s)
             if (c.peer_box[s]) { cudaIpcCloseMemHandle(c.peer_box[s]); c.peer_box[s] = nullptr; }
+        if (c.box) { cudaFree(c.box); c.box = nullptr; }
         if (std::getenv("SEM_B200_REQUIRE_P2P")) { set_error("peer-memory mailboxes unavailable (SEM_B200_REQUIRE_P2P set)"); return -5; }
     }
     return 0;
@@ -406,8 +409,10 @@ int comm_exchange_transfer(const Comm& c, const MeshDev& g, double* const* field
         if (!g.has_left && !g.has_right) return 0;
         return p2p_push(c, g, fields, nf, st);
     }
-    static const bool skip = std::getenv("SEM_B200_DEBUG_NO_TRANSFER") != nullptr;   // timing experiments only (wrong results)
+#ifdef SEM_DEBUG_HOOKS   // timing experiments only (wrong results): never part of the shipped library
+    static const bool skip = std::getenv("SEM_B200_DEBUG_NO_TRANSFER") != nullptr;
     if (skip) return 0;
+#endif
     if (nf > c.max_fields) { set_error("comm_exchange: too many fields"); return -2; }
     if (!g.has_left && !g.has_right) return 0;
     ncclComm_t comm = (ncclComm_t)c.nccl;

@@ -9,8 +9,15 @@
 #error "compile with -DSEM_P=<polynomial order>"
 #endif
 
+#define SEM_CAT2(a, b) a##b
+#define SEM_CAT(a, b) SEM_CAT2(a, b)
+
 namespace semb {
 
+// The round-1 v1 kernel (one column per thread, CTA barriers, LDG staging) is an independent second implementation kept for
+// A/B runs only: it is compiled in with `make V1=1` (-DSEM_WITH_V1) and selected with SEM_B200_MARCH=1; the default library
+// carries the v3 kernels only.
+#ifdef SEM_WITH_V1
 template <int P, int MODE>
 static int launch_mode(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
     const size_t smem = march_smem_doubles<P, MODE>(q.pitch) * sizeof(double);
@@ -25,9 +32,6 @@ static int launch_mode(const MeshDev& g, const MarchArgs& A, const MarchGeom& q,
     return 0;
 }
 
-#define SEM_CAT2(a, b) a##b
-#define SEM_CAT(a, b) SEM_CAT2(a, b)
-
 int SEM_CAT(march_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q,
                                    cudaStream_t st) {
     switch (mode) {
@@ -40,6 +44,12 @@ int SEM_CAT(march_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& 
     set_error("march_launch: unknown mode");
     return -2;
 }
+#else
+int SEM_CAT(march_launch_p, SEM_P)(int, const MeshDev&, const MarchArgs&, const MarchGeom&, cudaStream_t) {
+    set_error("the v1 marching kernel is not part of this build (make V1=1)");
+    return -2;
+}
+#endif
 
 // ---- v3 kernel (one warp per strip, TMA-staged, folded tables): every order, all modes.
 template <int P, int MODE, bool PW>

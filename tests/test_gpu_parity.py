@@ -282,6 +282,35 @@ def test_full_size_properties(sem):
     assert np.sqrt(d.dot(Kz, Kz)) <= 1e-12 * np.sqrt(d.dot(Kx, Kx))
 
 
+def test_full_size_against_kronecker_oracle(sem):
+    """BASELINE config 5 (1024 x 1024 elements, P = 8, 67.1M nodes per field) -- the benchmarked size -- against an oracle that is
+    NOT the kernel: the reference's operators through their Kronecker identities with sparse 1-D matrices on the host
+    (oracle.KronOps, itself pinned to the assembled reference operators on small meshes in tests/test_oracle.py).  Stiffness
+    apply, fused CD Jacobian apply and fused 3-field NS Jacobian apply, all rows (boundary rows included), <= 1e-12."""
+    from oracle import sem_oracle as so
+    P, ne = 8, 1024
+    k = so.KronOps(P, ne, ne, 1.0 / ne, 1.0 / ne)
+    sh = k.shape
+    rng = np.random.default_rng(5)
+    fields = [rng.standard_normal(sh[0] * sh[1]) for _ in range(5)]
+    x, u, v, dv, dp = fields
+    cd = sem.ConvectionDiffusionSolver(1.0, 1.0, 40.0, P, ne, ne, T_W=0.5, T_E=-0.5)
+    d = cd._dev
+    y = d.to_host(d.apply_stiffness(d.to_device(x), d.zeros()))
+    assert relerr(y, k.K(x.reshape(sh)).ravel()) < APPLY_TOL
+    cd._get_residuals(x, u, v)
+    ref = k.cd_jvp(40.0, x.reshape(sh), u.reshape(sh), v.reshape(sh), (1, 1, 0, 0)).ravel()
+    assert relerr(cd._get_dresiduals(x), ref) < APPLY_TOL                     # host-pipelined path (sem_cd_jvp_host)
+    del cd, d, y, ref
+    ns = sem.NavierStokesSolver(1.0, 1.0, 400.0, 0.0, P, ne, ne, u_N=1.0, iprint=[])
+    ns._get_residuals(u, v, x, np.zeros_like(x))
+    ns._calc_jacobians(u, v)
+    got = ns._get_dresiduals(x, dv, dp)
+    ref = k.ns_jvp(400.0, u.reshape(sh), v.reshape(sh), x.reshape(sh), dv.reshape(sh), dp.reshape(sh))
+    for a, b in zip(got, ref):
+        assert relerr(a, b.ravel()) < APPLY_TOL
+
+
 @pytest.mark.parametrize("bc", [dict(T_W=0.5, T_E=-0.5), dict(T_S=1.0), dict(T_W=0.2, T_E=0.1, T_S=-0.3, T_N=0.4),
                                 dict(T_N=0.5, T_E=0.0)])
 def test_fdm_preconditioner_matches_jacobi_and_is_mesh_independent(sem, bc):
@@ -414,3 +443,54 @@ def test_ns_preconditioner_levels_same_fields_fewer_iterations(sem, golden):
         its[precond] = sum(ns.krylov_iters)
     print("C2 Krylov iterations:", its)
     assert its["fdm+bb"] < 0.9 * its["fdm"] and its["full"] < 0.6 * its["fdm"], its
+
+
+@pytest.mark.parametrize("mode", ["GS", "JNK"])
+def test_reference_callers_on_the_drop_in(sem, golden, mode):
+    """The drop-in boundary, exercised with what the reference's OWN callers ask for: tests/golden/component_trace.npz is the
+    call trace (method, arguments, results) recorded while the UNMODIFIED OpenMDAO/*_Component.py adapters and the UNMODIFIED
+    OpenMDAO/Boussinesq_SequentialCoupler.run drove the reference's solvers (tests/golden/make_component_trace.py, openmdao
+    stand-in).  Replayed here, call by call and in order (the hidden state -- cached linearisation point, Jacobians -- follows
+    the same sequence), on the GPU classes: applies and interpolations <= 1e-12, linear / nonlinear solves <= 1e-8."""
+    g = golden("component_trace")
+    kw = {k[3:]: g[k].item() for k in g if k.startswith("kw/")}
+    Re, Ra, Pr = kw["Re"], kw["Ra"], kw["Pr"]
+    cd = sem.ConvectionDiffusionSolver(L_x=1.0, L_y=1.0, Pe=Re * Pr, P=int(kw["P_cd"]), N_ex=int(kw["N_ex_cd"]),
+                                       N_ey=int(kw["N_ey_cd"]), T_W=0.5, T_E=-0.5, mtol=1e-13)           # BSC:53-56
+    ns = sem.NavierStokesSolver(L_x=1.0, L_y=1.0, Re=Re, Gr=Ra / Pr, P=int(kw["P_ns"]), N_ex=int(kw["N_ex_ns"]),
+                                N_ey=int(kw["N_ey_ns"]), mtol=1e-13, mtol_newton=1e-13, iprint=[])        # BSC:57-59
+    who = {"cd": cd, "ns": ns}
+    n = int(g[f"{mode}/n"])
+    worst = {}
+    for i in range(n):
+        tag, name = str(g[f"{mode}/{i}/who"]).split(".")
+        nargs = 1 + max([int(k.rsplit("arg", 1)[1]) for k in g if k.startswith(f"{mode}/{i}/arg")] + [-1])
+        args = [g.get(f"{mode}/{i}/arg{j}") for j in range(nargs)]
+        kwargs = {k.rsplit("kw_", 1)[1]: g[k] for k in g if k.startswith(f"{mode}/{i}/kw_")}
+        if name == "_get_interpol":                       # second argument: the (x, y) mesh grid, stored as one [2, nx, ny] array
+            args[1] = (args[1][0], args[1][1])
+        args = [a.copy() if isinstance(a, np.ndarray) else a for a in args]
+        out = getattr(who[tag], name)(*args, **{k: v.copy() for k, v in kwargs.items()})
+        outs = () if out is None else (out if isinstance(out, tuple) else (out,))
+        refs = [g[f"{mode}/{i}/out{j}"] for j in range(len(outs))]
+        assert len(refs) == sum(1 for k in g if k.startswith(f"{mode}/{i}/out")), f"{tag}.{name}: number of results"
+        tol = FIELD_TOL if name in ("_get_update", "_get_solution") else APPLY_TOL
+        # scale of an apply: its result, or -- for the residuals of a converged state, which are rounding noise on both sides --
+        # the size of what went in
+        in_scale = max([float(np.linalg.norm(a)) for a in args if isinstance(a, np.ndarray)] + [0.0])
+        for o, r in zip(outs, refs):
+            nr = max(float(np.linalg.norm(r)), in_scale if tol == APPLY_TOL else 0.0)
+            err = np.linalg.norm(np.asarray(o).reshape(r.shape) - r) / (nr if nr > 1e-30 else 1.0)
+            worst[name] = max(worst.get(name, 0.0), err)
+            assert err < tol, f"call {i}: {tag}.{name} differs from the reference by {err:.2e}"
+    print(mode, "worst relative differences per method:", {k: f"{v:.1e}" for k, v in worst.items()})
+    xp, yp = g["xp"], g["yp"]
+    assert relerr(cd._get_interpol(T_last(g, mode, n), (xp, yp)), g[f"{mode}/T_plot"]) < 1e-10
+
+
+def T_last(g, mode, n):
+    """The temperature the coupler handed to the final ``cd._get_interpol`` call of the trace."""
+    for i in range(n - 1, -1, -1):
+        if str(g[f"{mode}/{i}/who"]) == "cd._get_interpol":
+            return g[f"{mode}/{i}/arg0"]
+    raise AssertionError("trace holds no cd._get_interpol call")

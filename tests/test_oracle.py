@@ -107,6 +107,45 @@ def test_ns_matches_reference(golden, tag, kw, solve):
     assert relerr(a, k("upd_u")) < 1e-7 and relerr(b, k("upd_v")) < 1e-7 and relerr(c, k("upd_p")) < 1e-5
 
 
+@pytest.mark.parametrize("P,nx,ny,Lx,Ly", [(4, 5, 3, 1.3, 0.7), (3, 4, 4, 1.0, 1.0), (8, 3, 2, 2.0, 1.0)])
+def test_kronecker_operators_match_the_assembled_ones(P, nx, ny, Lx, Ly):
+    """oracle.KronOps (the full-size checker of tests/test_gpu_parity.py::test_full_size_against_kronecker_oracle) reproduces the
+    assembled operators / Jacobian-vector products of the pinned oracle classes."""
+    k = so.KronOps(P, nx, ny, Lx / nx, Ly / ny)
+    sh = k.shape
+    cd = so.CDOracle(Lx, Ly, 7.0, P, nx, ny, T_W=0.5, T_E=-0.5, T_S=0.2)
+    rng = np.random.default_rng(0)
+    T, u, v, p, a, b, c = (rng.standard_normal(cd.N) for _ in range(7))
+    M, K, Gx, Gy = so.global_operators(P, nx, ny, Lx / nx, Ly / ny)
+    assert relerr(k.K(a.reshape(sh)).ravel(), K @ a) < 1e-14 and relerr(k.Gx(a.reshape(sh)).ravel(), Gx @ a) < 1e-14
+    assert relerr(k.Gy(a.reshape(sh)).ravel(), Gy @ a) < 1e-14 and relerr(k.M(a.reshape(sh)).ravel(), M * a) < 1e-14
+    cd._get_residuals(T, u, v)
+    assert relerr(k.cd_jvp(7.0, a.reshape(sh), u.reshape(sh), v.reshape(sh), (1, 1, 1, 0)).ravel(), cd._get_dresiduals(a)) < 1e-14
+    ns = so.NSOracle(Lx, Ly, 30.0, 0.0, P, nx, ny, u_N=1.0)
+    ns._get_residuals(u, v, p, T)
+    ns._calc_jacobians(u, v)
+    got = k.ns_jvp(30.0, u.reshape(sh), v.reshape(sh), a.reshape(sh), b.reshape(sh), c.reshape(sh))
+    for x, y in zip(got, ns._get_dresiduals(a, b, c)):
+        assert relerr(x.ravel(), y) < 1e-14
+
+
+def test_reference_algorithm_ports_reach_the_direct_solution():
+    """The line-by-line ports of the reference's own linear solvers (SciPy LGMRES on the CD operator, CD:123-156; SuperLU +
+    LGMRES on the pressure Schur complement, NS:162-236) -- the host timing baselines of bench.py -- land on the oracle's
+    direct solution, and the NS port needs the number of Schur evaluations the survey probed on the reference."""
+    kw = dict(L_x=1.0, L_y=1.0, Pe=40.0, P=4, N_ex=8, N_ey=8, T_W=0.5, T_E=-0.5)
+    cd = so.CDOracle(mtol=1e-12, **kw)
+    u = cd._get_vector(lambda x, y: y - 0.5)
+    v = cd._get_vector(lambda x, y: 0.5 - x)
+    T, evals = cd._get_solution_lgmres(u, v)
+    assert relerr(T, cd._get_solution(u, v)) < 1e-9 and evals > 50
+    ns = so.NSOracle(1.0, 1.0, 100.0, 0.0, 4, 6, 6, u_N=1.0, mtol=1e-12, mtol_newton=1e-11)
+    ua, va, pa = ns._get_solution(np.zeros(ns.N), algorithm='reference')
+    ns2 = so.NSOracle(1.0, 1.0, 100.0, 0.0, 4, 6, 6, u_N=1.0, mtol=1e-12, mtol_newton=1e-11)
+    ub, vb, pb = ns2._get_solution(np.zeros(ns.N))
+    assert ns._k == ns2._k and relerr(ua, ub) < 1e-8 and relerr(va, vb) < 1e-8 and relerr(pa, pb) < 1e-7
+
+
 def test_readme_helmholtz_known_answer():
     """Solvers/README.md:49-96: (lambda M + K) u = M f with f = cos(pi x/Lx) cos(pi y/Ly), homogeneous Neumann;
     exact u = f / (lambda + pi^2 (1/Lx^2 + 1/Ly^2)).  Max error 9.5e-7 at P=4, 2x3 elements."""
