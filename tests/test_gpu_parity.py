@@ -478,9 +478,17 @@ def test_reference_callers_on_the_drop_in(sem, golden, mode):
         # scale of an apply: its result, or -- for the residuals of a converged state, which are rounding noise on both sides --
         # the size of what went in
         in_scale = max([float(np.linalg.norm(a)) for a in args if isinstance(a, np.ndarray)] + [0.0])
+        if name == "_get_update" and in_scale <= 10.0 * 1e-13 * np.sqrt(who[tag].N):
+            # a right-hand side below the solvers' own stopping threshold mtol sqrt(N) (CD:147, NS:223): every small vector is a
+            # valid answer (the reference returns its initial guess); only check that nothing large comes back
+            assert all(np.linalg.norm(o) <= 1e4 * in_scale for o in outs), f"call {i}: {tag}.{name} on a noise-level right-hand side"
+            continue
+        # both sides stop a linear solve at the ABSOLUTE residual mtol sqrt(N) (CD:147, NS:223), so two valid answers may differ by
+        # ~ atol |J^-1|: allow 1e3 atol on top of the relative bar (matters for the small right-hand sides of late Newton steps)
+        slack = 1e3 * 1e-13 * np.sqrt(who[tag].N) if name == "_get_update" else 0.0
         for o, r in zip(outs, refs):
             nr = max(float(np.linalg.norm(r)), in_scale if tol == APPLY_TOL else 0.0)
-            err = np.linalg.norm(np.asarray(o).reshape(r.shape) - r) / (nr if nr > 1e-30 else 1.0)
+            err = max(np.linalg.norm(np.asarray(o).reshape(r.shape) - r) - slack, 0.0) / (nr if nr > 1e-30 else 1.0)
             worst[name] = max(worst.get(name, 0.0), err)
             assert err < tol, f"call {i}: {tag}.{name} differs from the reference by {err:.2e}"
     print(mode, "worst relative differences per method:", {k: f"{v:.1e}" for k, v in worst.items()})
