@@ -16,7 +16,9 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'lts__t_sector_hit_rate.pct', 'sass__inst_executed_register_spilling', 'sass__inst_executed_global_loads',
         'sass__inst_executed_global_stores', 'sass__inst_executed_shared_loads', 'sass__inst_executed_shared_stores',
-        'smsp__warps_eligible.avg.per_cycle_active']
+        'smsp__warps_eligible.avg.per_cycle_active',
+        'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+        'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed']
 want += [h for h in hdr if 'smsp__average_warps_issue_stalled' in h and h.endswith('per_issue_active.ratio')]
 res = []
 for r in rows[2:]:
