@@ -207,6 +207,38 @@ int sem_ns_solve(sem_ctx *ctx, const sem_ns_state *st, const double *rhs3, doubl
 int sem_ns_precond_debug(sem_ctx *ctx, const sem_ns_state *st, int what, int level, const double *in, const double *in2,
                          double *out, void *stream);
 
+/* ---- coupled Boussinesq system on the device: the linear solve of the OpenMDAO Newton-Krylov coupling
+ * (OpenMDAO/Boussinesq_SequentialCoupler.py:75-94: ScipyKrylov GMRES(restart) on apply_linear, one block-Jacobi sweep of
+ * solve_linear as preconditioner).  Coupled vectors are [dT (CD mesh vec) | du | dv | dp (NS mesh vecs)], device resident.
+ * sem_transfer: tables of the mesh-to-mesh interpolation (change_inputs, CD_Component.py:23-36, NS_Component.py:23-33) onto
+ * EVERY node of the target mesh -- element column / row of each target line (mx[nxp], ny[nyp]) and Lagrange basis values
+ * (Sx [nxp][P+1], Sy [nyp][P+1]) of the SOURCE mesh, DEVICE arrays as for sem_interpolate.  One GPU. */
+typedef struct {
+    int nxp, nyp;
+    const int *mx, *ny;
+    const double *Sx, *Sy;
+} sem_transfer;
+typedef struct {
+    sem_ctx *ns, *cd;
+    const sem_ns_state *ns_state;      /* linearisation point incl. Jacobian diagonals (after _get_residuals + _calc_jacobians) */
+    const sem_cd_state *cd_state;      /* incl. gxT, gyT */
+    sem_transfer ns_to_cd, cd_to_ns;
+    const sem_krylov *kr_ns, *kr_cd;   /* controls of the inner (block) solves */
+    double *ns_work; long long ns_work_len;     /* work buffers of the inner solves (sem_ns_work_len / sem_cd_work_len) */
+    double *cd_work; long long cd_work_len;
+    const double *ns_null;             /* 3 NS vecs: left null vector of the NS Jacobian, or NULL (regular Jacobian) */
+    double ns_null_nrm2;
+    /* outputs of sem_coupled_solve */
+    int iters_cd, iters_ns, solves;
+} sem_coupled;
+long long sem_coupled_vec_len(const sem_coupled *q);
+long long sem_coupled_work_len(const sem_coupled *q, int restart);
+/* y = J x; scratch: 2 CD vecs + 1 NS vec */
+int sem_coupled_jvp(const sem_coupled *q, const double *x, double *y, double *scratch, void *stream);
+/* solve J x = rhs (x holds the guess); `outer`: a context on the NS mesh whose reduction scratch serves the outer iteration */
+int sem_coupled_solve(sem_ctx *outer, sem_coupled *q, const double *rhs, double *x, sem_krylov *kr, double *work,
+                      long long work_len, void *stream);
+
 /* ---- reductions used by the Python layer (deterministic two-stage sums) ---------------------------------------- */
 /* n = (number of fields) * sem_ctx_vec_len(); interface lines are counted once and the sum is global over ranks */
 int sem_dot(sem_ctx *ctx, const double *x, const double *y, long long n, double *host_out, void *stream);

@@ -16,6 +16,10 @@ same tolerances and the same component semantics, calling the GPU solvers direct
 
 The mesh-to-mesh transfer between the CD and NS spaces (``change_inputs``, ``CD_Component.py:23-36``) is the tensor-product
 interpolation ``I_x F I_y^T`` on the device (``SemDevice.interpolate``); it is skipped when both meshes coincide.
+
+With the GPU solvers the linear solve of ``mode='JNK'`` is device resident (``sem_coupled_solve``): coupled vector, Krylov basis,
+operator kernels, mesh transfers and both inner block solves stay in HBM.  The host-vector GMRES below remains for solver
+objects without a device (the CPU check of this module's logic in tests/test_oracle.py).
 """
 import typing
 
@@ -57,6 +61,73 @@ class _Coupled:
         T, u, v, p = self.split(x)
         self.cd._calc_jacobians(T)
         self.ns._calc_jacobians(u, v)
+
+    # ---- the linear solve of the Newton-Krylov coupling on the device (sem_coupled_solve) ------------------------------------
+    def device_ready(self):
+        """Both solvers are the GPU classes on one (unpartitioned) device."""
+        return all(getattr(s, '_dev', None) is not None and s._dev.part is None for s in (self.cd, self.ns))
+
+    def device_solve(self, rhs, atol, restart, maxiter):
+        """GMRES(restart) on the coupled Jacobian with one block-Jacobi sweep as preconditioner (BSC:91-94), entirely on the
+        device: the coupled vector [dT | du | dv | dp], the Krylov basis, both operator kernels, the mesh-to-mesh transfers and
+        the two inner block solves stay in HBM; per iteration only the Hessenberg column travels to the host.  Must follow
+        ``residual`` + ``linearize`` (they set the linearisation state of both solvers).  Returns (dx, iterations)."""
+        import ctypes as C
+        import torch
+        from . import SEM
+        from . import _lib as L
+        from .device import SemDevice
+        cd, ns = self.cd, self.ns
+        dc, dn = cd._dev, ns._dev
+        if not hasattr(self, '_dev_state'):
+            tabs = []
+            for src, dst in ((ns, cd), (cd, ns)):
+                xs = SEM.global_nodes_1d(dst._P, dst._N_ex, dst._dx)
+                ys = SEM.global_nodes_1d(dst._P, dst._N_ey, dst._dy)
+                tabs.append(src._dev.transfer_tables(xs, ys))
+            outer = SemDevice(ns._P, ns._N_ex, ns._N_ey, ns._dx, ns._dy, device=dn.device)
+            ns._krylov()
+            if not dn.has_ns_schur:
+                dn.setup_ns_schur(int(ns.N / 2))
+            null = dn.ns_left_null_vector()
+            self._dev_state = dict(tabs=tabs, outer=outer, null=null, nrm2=dn.dot(null, null) if null is not None else 0.0, work=None)
+        S = self._dev_state
+        kr_ns, kr_cd = ns._krylov(), cd._krylov()
+        st_ns, st_cd = ns._state(), cd._state()
+        q = L.sem_coupled()
+        q.ns, q.cd = dn.ctx, dc.ctx
+        q.ns_state, q.cd_state = C.pointer(st_ns), C.pointer(st_cd)
+        for name, (mx, Sx, ny, Sy), dst in (("ns_to_cd", S["tabs"][0], dc), ("cd_to_ns", S["tabs"][1], dn)):
+            setattr(q, name, L.sem_transfer(dst.NX, dst.NY, mx.data_ptr(), ny.data_ptr(), Sx.data_ptr(), Sy.data_ptr()))
+        q.kr_ns, q.kr_cd = C.pointer(kr_ns), C.pointer(kr_cd)
+        q.ns_work, q.ns_work_len = ns._work.data_ptr(), ns._work.numel()
+        q.cd_work, q.cd_work_len = cd._work.data_ptr(), cd._work.numel()
+        q.ns_null = S["null"].data_ptr() if S["null"] is not None else None
+        q.ns_null_nrm2 = float(S["nrm2"])
+        lib = dn.lib
+        n = lib.sem_coupled_vec_len(C.byref(q))
+        need = lib.sem_coupled_work_len(C.byref(q), int(restart))
+        if S["work"] is None or S["work"].numel() < need + 2 * n:
+            S["work"] = torch.zeros(need + 2 * n, dtype=torch.float64, device=dn.tdev)
+        b, x, work = S["work"][:n], S["work"][n:2 * n], S["work"][2 * n:]
+        x.zero_()
+        vc, vn = dc.vec_len, dn.vec_len
+        parts = self.split(rhs)
+        dc.to_device(parts[0], b[:vc].view(dc.NX, dc.LD))
+        for k in range(3):
+            dn.to_device(parts[1 + k], b[vc + k * vn:vc + (k + 1) * vn].view(dn.NX, dn.LD))
+        kr = L.sem_krylov()
+        kr.atol, kr.restart, kr.max_iters, kr.precond, kr.verbose = float(atol), int(restart), int(maxiter), 0, 0
+        code = L.check(lib.sem_coupled_solve(S["outer"].ctx, C.byref(q), b.data_ptr(), x.data_ptr(), C.byref(kr), work.data_ptr(),
+                                             work.numel(), dn.stream), "sem_coupled_solve")
+        self.iter_cd += q.solves
+        self.iter_ns += q.solves
+        ns.krylov_iters.append(q.iters_ns)
+        if code != 0:
+            raise RuntimeError(f'Boussinesq GMRES: Failed to converge in {kr.iters} iterations')
+        dx = np.concatenate([dc.to_host(x[:vc].view(dc.NX, dc.LD))] +
+                            [dn.to_host(x[vc + k * vn:vc + (k + 1) * vn].view(dn.NX, dn.LD)) for k in range(3)])
+        return dx, kr.iters
 
     def jvp(self, dx):
         """apply_linear of both components (forward mode)."""
@@ -161,8 +232,14 @@ def solve(cd: ConvectionDiffusionSolver, ns: NavierStokesSolver, mode='JNK', mto
             if rn <= atol_nonlin:
                 break
             sys_.linearize(x)
-            if mode == 'JNK':
-                dx, its = _gmres(sys_.jvp, sys_.block_jacobi, -r, atol_gmres, restart, 5000)    # BSC:91-94
+            if mode == 'JNK' and sys_.device_ready():
+                dx, its = sys_.device_solve(-r, atol_gmres, restart, 5000)                      # BSC:91-94, device resident
+                info['gmres_its'].append(its)
+                x = x + dx
+                r = sys_.residual(x)
+                rn = np.linalg.norm(r)
+            elif mode == 'JNK':
+                dx, its = _gmres(sys_.jvp, sys_.block_jacobi, -r, atol_gmres, restart, 5000)    # host vectors (CPU checks)
                 info['gmres_its'].append(its)
                 x = x + dx
                 r = sys_.residual(x)

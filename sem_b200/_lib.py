@@ -50,9 +50,21 @@ class sem_ns_schur_desc(C.Structure):
                 ("inv_den", C.c_double), ("cheb_lo", C.c_double), ("cheb_hi", C.c_double), ("cheb_steps", C.c_int)]
 
 
+class sem_transfer(C.Structure):
+    _fields_ = [("nxp", C.c_int), ("nyp", C.c_int), ("mx", C.c_void_p), ("ny", C.c_void_p), ("Sx", C.c_void_p), ("Sy", C.c_void_p)]
+
+
 class sem_krylov(C.Structure):
     _fields_ = [("atol", C.c_double), ("restart", C.c_int), ("max_iters", C.c_int), ("precond", C.c_int),
                 ("verbose", C.c_int), ("iters", C.c_int), ("resnorm", C.c_double)]
+
+
+class sem_coupled(C.Structure):
+    _fields_ = [("ns", C.c_void_p), ("cd", C.c_void_p), ("ns_state", C.POINTER(sem_ns_state)), ("cd_state", C.POINTER(sem_cd_state)),
+                ("ns_to_cd", sem_transfer), ("cd_to_ns", sem_transfer), ("kr_ns", C.POINTER(sem_krylov)),
+                ("kr_cd", C.POINTER(sem_krylov)), ("ns_work", C.c_void_p), ("ns_work_len", C.c_longlong),
+                ("cd_work", C.c_void_p), ("cd_work_len", C.c_longlong), ("ns_null", C.c_void_p), ("ns_null_nrm2", C.c_double),
+                ("iters_cd", C.c_int), ("iters_ns", C.c_int), ("solves", C.c_int)]
 
 
 _P = C.c_void_p
@@ -95,6 +107,10 @@ SIGNATURES = {
     "sem_ns_jvp": (C.c_int, [_P, C.POINTER(sem_ns_state), _P, _P, _P, _P, _P, _P, _P, _P]),
     "sem_ns_work_len": (_LL, [_P, C.c_int]),
     "sem_ns_solve": (C.c_int, [_P, C.POINTER(sem_ns_state), _P, _P, C.POINTER(sem_krylov), _P, _LL, _P]),
+    "sem_coupled_vec_len": (_LL, [C.POINTER(sem_coupled)]),
+    "sem_coupled_work_len": (_LL, [C.POINTER(sem_coupled), C.c_int]),
+    "sem_coupled_jvp": (C.c_int, [C.POINTER(sem_coupled), _P, _P, _P, _P]),
+    "sem_coupled_solve": (C.c_int, [_P, C.POINTER(sem_coupled), _P, _P, C.POINTER(sem_krylov), _P, _LL, _P]),
     "sem_dot": (C.c_int, [_P, _P, _P, _LL, C.POINTER(C.c_double), _P]),
     "sem_axpby": (C.c_int, [_P, C.c_double, _P, C.c_double, _P, _LL, _P]),
 }

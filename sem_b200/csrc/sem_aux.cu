@@ -518,7 +518,7 @@ int aux_sub(const double* a, const double* b, double* out, long long n, cudaStre
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_interpolate(const MeshDev g, const double* __restrict__ f, int nxp, const int* __restrict__ mx,
                               const double* __restrict__ Sx, int nyp, const int* __restrict__ ny, const double* __restrict__ Sy,
-                              double* __restrict__ out) {
+                              double* __restrict__ out, int ldo) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = blockIdx.y;
     if (b >= nyp) return;
@@ -533,12 +533,23 @@ __global__ void k_interpolate(const MeshDev g, const double* __restrict__ f, int
             val = fma(Sx[a * n1 + i], row, val);
         }
     }
-    out[(size_t)a * nyp + b] = val;
+    out[(size_t)a * ldo + b] = val;
 }
 int aux_interpolate(const MeshDev& g, const double* f, int nxp, const int* mx, const double* Sx, int nyp, const int* ny,
-                    const double* Sy, double* out, cudaStream_t st) {
+                    const double* Sy, double* out, int ldo, cudaStream_t st) {
     if (nxp <= 0 || nyp <= 0) return 0;
-    k_interpolate<<<dim3((unsigned)((nyp + 127) / 128), (unsigned)nxp), 128, 0, st>>>(g, f, nxp, mx, Sx, nyp, ny, Sy, out);
+    k_interpolate<<<dim3((unsigned)((nyp + 127) / 128), (unsigned)nxp), 128, 0, st>>>(g, f, nxp, mx, Sx, nyp, ny, Sy, out, ldo);
+    SEM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// y += scale * (*coef) * x with the coefficient on the device (projection b - l (l.b) / (l.l) without a host round trip)
+__global__ void k_axpy_dev(long long n, const double* __restrict__ x, const double* __restrict__ coef, double scale, double* __restrict__ y) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fma(scale * *coef, x[i], y[i]);
+}
+int aux_axpy_dev(long long n, const double* x, const double* coef, double scale, double* y, cudaStream_t st) {
+    k_axpy_dev<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, x, coef, scale, y);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }

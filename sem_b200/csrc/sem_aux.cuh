@@ -73,7 +73,9 @@ int aux_ns_schur_mass(const MeshDev& g, TabDev t, const double* rc, const double
 
 // SEM.eval_interpolation on an ij-meshgrid (SEM.py:248-273): see k_interpolate
 int aux_interpolate(const MeshDev& g, const double* f, int nxp, const int* mx, const double* Sx, int nyp, const int* ny,
-                    const double* Sy, double* out, cudaStream_t st);
+                    const double* Sy, double* out, int ldo, cudaStream_t st);
+// y += scale * (*coef) * x, coefficient on the device
+int aux_axpy_dev(long long n, const double* x, const double* coef, double scale, double* y, cudaStream_t st);
 // out = a - b
 int aux_sub(const double* a, const double* b, double* out, long long n, cudaStream_t st);
 

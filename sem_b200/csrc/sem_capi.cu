@@ -563,7 +563,7 @@ extern "C" int sem_interpolate(sem_ctx* c, const double* vec, int nxp, const int
                                const double* Sy, double* out, void* stream) {
     SEM_CHECK_CTX(c);
     cudaStream_t st = (cudaStream_t)stream;
-    if (aux_interpolate(c->g, vec, nxp, mx, Sx, nyp, ny, Sy, out, st)) return -1;
+    if (aux_interpolate(c->g, vec, nxp, mx, Sx, nyp, ny, Sy, out, nyp, st)) return -1;
     if (c->has_comm) return comm_allreduce_sum(c->comm, out, nxp * nyp, st);
     return 0;
 }
@@ -1103,8 +1103,12 @@ struct GmresLayout {
     long long vlen;  // doubles per field
 };
 
+// Z != nullptr: FLEXIBLE GMRES -- the preconditioned vectors Z_j = Pinv(V_j) are kept (restart vectors of n doubles) and the
+// solution is updated as x += Z y instead of x += Pinv(V y).  Needed when Pinv is only approximately linear (an inner Krylov
+// solve to a tolerance): otherwise the true residual stalls at the inner tolerance while the Arnoldi estimate keeps falling.
 static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop& Pinv, const double* b, double* x,
-                 sem_krylov* kr, double* V, double* w, double* t, double* vin, cudaStream_t st, bool use_graph) {
+                 sem_krylov* kr, double* V, double* w, double* t, double* vin, cudaStream_t st, bool use_graph,
+                 double* Z = nullptr) {
     const long long n = L.n;
     int m = kr->restart;
     if (m < 1) m = 1;
@@ -1176,6 +1180,7 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
         bool stop = false;
         auto enqueue_step = [&](int j) -> int {
             if (apply_fixed()) return -1;   // w = A Pinv(V_j), V_j read through its copy vin
+            if (Z && aux_axpby(1.0, t, 0.0, Z + (long long)j * n, n, st)) return -1;
             double* h1 = c->d_small;
             double* h2 = c->d_small + (j + 1);
             double* nr = c->d_small + 2 * (j + 1);
@@ -1239,8 +1244,12 @@ static int gmres(sem_ctx* c, const GmresLayout& L, const vecop& Aop, const vecop
         }
         std::memcpy(c->h_small, yv.data(), sizeof(double) * k);
         SEM_CUDA(cudaMemcpyAsync(c->d_small, c->h_small, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        if (aux_multi_comb(V, n, k, c->d_small, w, c->rs, st)) return -1;
-        if (Pinv(w, t)) return -1;
+        if (Z) {
+            if (aux_multi_comb(Z, n, k, c->d_small, t, c->rs, st)) return -1;
+        } else {
+            if (aux_multi_comb(V, n, k, c->d_small, w, c->rs, st)) return -1;
+            if (Pinv(w, t)) return -1;
+        }
         if (aux_axpby(1.0, t, 1.0, x, n, st)) return -1;
         // true residual
         if (Aop(x, w)) return -1;
@@ -1340,6 +1349,93 @@ extern "C" int sem_ns_solve(sem_ctx* c, const sem_ns_state* s, const double* rhs
     vecop Pinv = [&](const double* r, double* z) { return ns_precond_apply(c, lin, kr->precond, r, z, tmp, st); };
     GmresLayout L{n, 3, vlen};
     const int rc = gmres(c, L, Aop, Pinv, rhs3, x3, kr, V, w, t, vin, st, use_graph);
+    SEM_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coupled Boussinesq system on the device (reference: the OpenMDAO Newton-Krylov of
+// OpenMDAO/Boussinesq_SequentialCoupler.py:75-94 -- ScipyKrylov GMRES(restart) on apply_linear with one block-Jacobi sweep of
+// solve_linear as preconditioner).  The coupled vector is [dT (CD mesh) | du | dv | dp (NS mesh)]; the Jacobian-vector
+// product is the two fused operator kernels with the fields moved between the two meshes by the interpolation kernel
+// (change_inputs, CD_Component.py:23-36 / NS_Component.py:23-33); the preconditioner is one CD solve and one NS solve (right-hand
+// side projected onto the range of the singular NS Jacobian).  Everything stays in HBM: per Krylov iteration only the small
+// Hessenberg columns travel to the host.  One GPU (both solvers in this process); `outer` is a context on the NS mesh whose
+// reduction scratch serves the outer iteration (the inner solves use the scratch of their own contexts).
+// ---------------------------------------------------------------------------------------------------------------
+static int transfer(sem_ctx* from, sem_ctx* to, const sem_transfer& t, const double* src, double* dst, cudaStream_t st) {
+    if (t.nxp != to->g.NX || t.nyp != to->g.NY) { set_error("sem_coupled: transfer table does not match the target mesh"); return -2; }
+    return aux_interpolate(from->g, src, t.nxp, t.mx, t.Sx, t.nyp, t.ny, t.Sy, dst, to->g.LD, st);
+}
+
+extern "C" long long sem_coupled_vec_len(const sem_coupled* q) {
+    if (!q || !q->ns || !q->cd) return -1;
+    return (long long)q->cd->g.NX * q->cd->g.LD + 3ll * q->ns->g.NX * q->ns->g.LD;
+}
+extern "C" long long sem_coupled_work_len(const sem_coupled* q, int restart) {
+    const long long n = sem_coupled_vec_len(q);
+    if (n < 0) return -1;
+    // basis + preconditioned basis (flexible GMRES) + w, t, vin; scratch: 2 CD vecs (u, v on the CD mesh), 1 NS vec (T on the NS
+    // mesh), 3 NS vecs (projected right-hand side)
+    return (long long)(2 * restart + 1 + 3) * n + 2ll * q->cd->g.NX * q->cd->g.LD + 4ll * q->ns->g.NX * q->ns->g.LD;
+}
+
+static int coupled_jvp(const sem_coupled* q, double* scratch, const double* x, double* y, cudaStream_t st) {
+    const long long vc = (long long)q->cd->g.NX * q->cd->g.LD, vn = (long long)q->ns->g.NX * q->ns->g.LD;
+    const double *dT = x, *du = x + vc, *dv = du + vn, *dp = dv + vn;
+    double *uc = scratch, *vcd = scratch + vc, *Tn = scratch + 2 * vc;
+    if (transfer(q->ns, q->cd, q->ns_to_cd, du, uc, st) || transfer(q->ns, q->cd, q->ns_to_cd, dv, vcd, st)) return -1;
+    if (transfer(q->cd, q->ns, q->cd_to_ns, dT, Tn, st)) return -1;
+    if (sem_cd_jvp(q->cd, q->cd_state, dT, uc, vcd, y, (void*)st)) return -1;
+    return sem_ns_jvp(q->ns, q->ns_state, du, dv, dp, Tn, y + vc, y + vc + vn, y + vc + 2 * vn, (void*)st);
+}
+
+extern "C" int sem_coupled_jvp(const sem_coupled* q, const double* x, double* y, double* scratch, void* stream) {
+    if (!q || !q->ns || !q->cd) { set_error("sem_coupled_jvp: null argument"); return -2; }
+    SEM_CUDA(cudaSetDevice(q->ns->device));
+    return coupled_jvp(q, scratch, x, y, (cudaStream_t)stream);
+}
+
+extern "C" int sem_coupled_solve(sem_ctx* outer, sem_coupled* q, const double* rhs, double* x, sem_krylov* kr, double* work,
+                                 long long work_len, void* stream) {
+    SEM_CHECK_CTX(outer);
+    if (!q || !q->ns || !q->cd || !q->kr_ns || !q->kr_cd) { set_error("sem_coupled_solve: null argument"); return -2; }
+    if (outer->has_comm || q->ns->has_comm || q->cd->has_comm) { set_error("sem_coupled_solve: one GPU only"); return -2; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long vc = (long long)q->cd->g.NX * q->cd->g.LD, vn = (long long)q->ns->g.NX * q->ns->g.LD, n = vc + 3 * vn;
+    if (kr->restart > SEM_MAX_RESTART) kr->restart = SEM_MAX_RESTART;
+    if (work_len < sem_coupled_work_len(q, kr->restart)) { set_error("sem_coupled_solve: work buffer too small"); return -2; }
+    double* V = work;
+    double* Z = work + (long long)(kr->restart + 1) * n;   // flexible GMRES: the block solves are Krylov solves to a tolerance
+    double* w = Z + (long long)kr->restart * n;
+    double* t = w + n;
+    double* vin = t + n;
+    double* scratch = vin + n;                 // 2 CD vecs + 1 NS vec
+    double* proj = scratch + 2 * vc + vn;      // 3 NS vecs
+    SEM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (3 * n + 2 * vc + 4 * vn), st));
+    q->iters_cd = q->iters_ns = q->solves = 0;
+    vecop Aop = [&](const double* xx, double* yy) { return coupled_jvp(q, scratch, xx, yy, st); };
+    vecop Pinv = [&](const double* r, double* z) {
+        // LinearBlockJac, one sweep, zero initial guess (BSC:89,94): solve_linear of each component
+        SEM_CUDA(cudaMemsetAsync(z, 0, sizeof(double) * n, st));
+        sem_krylov kc = *q->kr_cd;
+        int rc = sem_cd_solve(q->cd, q->cd_state, r, z, &kc, q->cd_work, q->cd_work_len, (void*)st);
+        q->iters_cd += kc.iters;
+        if (rc) { if (rc > 0) set_error("sem_coupled_solve: the CD block solve did not converge"); return rc > 0 ? -6 : rc; }
+        SEM_CUDA(cudaMemcpyAsync(proj, r + vc, sizeof(double) * 3 * vn, cudaMemcpyDeviceToDevice, st));
+        if (q->ns_null) {   // b <- b - l (l.b) / (l.l): the NS block is singular, a Krylov vector need not lie in its range
+            if (ctx_multi_dot(q->ns, q->ns_null, 3 * vn, 1, proj, q->ns->d_small, 3, vn, st)) return -1;
+            if (aux_axpy_dev(3 * vn, q->ns_null, q->ns->d_small, -1.0 / q->ns_null_nrm2, proj, st)) return -1;
+        }
+        sem_krylov kn = *q->kr_ns;
+        rc = sem_ns_solve(q->ns, q->ns_state, proj, z + vc, &kn, q->ns_work, q->ns_work_len, (void*)st);
+        q->iters_ns += kn.iters;
+        q->solves += 1;
+        if (rc) { if (rc > 0) set_error("sem_coupled_solve: the NS block solve did not converge"); return rc > 0 ? -6 : rc; }
+        return 0;
+    };
+    GmresLayout L{n, 1, n};
+    const int rc = gmres(outer, L, Aop, Pinv, rhs, x, kr, V, w, t, vin, st, false, Z);
     SEM_CUDA(cudaStreamSynchronize(st));
     return rc;
 }

@@ -161,19 +161,24 @@ class SemDevice:
         SEM.py:248-273) by the tensor-product kernel ``sem_interpolate``: the element of every plot column / row comes from
         ``x2xi`` (SEM.py:23-36) and the Lagrange basis values from ``GLL.standard_evaluation_matrix`` (GLL.py:105-116), like
         the reference.  Works on a partitioned mesh too (every rank gets the whole array)."""
-        from . import SEM
         xs, ys = np.asarray(xs, dtype=np.float64).ravel(), np.asarray(ys, dtype=np.float64).ravel()
-        tabs = []
-        for pts, h, nel in ((xs, self.dx, self.N_ex), (ys, self.dy, self.N_ey)):
-            e, xi = SEM.x2xi(pts, h)
-            e = np.clip(e, 0, nel - 1)
-            S = GLL.standard_evaluation_matrix(self.P, xi)
-            tabs.append((torch.from_numpy(e.astype(np.int32)).to(self.tdev), torch.from_numpy(np.ascontiguousarray(S)).to(self.tdev)))
-        (mx, Sx), (ny, Sy) = tabs
+        mx, Sx, ny, Sy = self.transfer_tables(xs, ys)
         out = torch.empty((xs.size, ys.size), dtype=torch.float64, device=self.tdev)
         L.check(self.lib.sem_interpolate(self.ctx, vec.data_ptr(), int(xs.size), mx.data_ptr(), Sx.data_ptr(), int(ys.size),
                                          ny.data_ptr(), Sy.data_ptr(), out.data_ptr(), self.stream), "sem_interpolate")
         return out.cpu().numpy()
+
+    def transfer_tables(self, xs, ys):
+        """Device tables of the interpolation from THIS mesh onto the tensor grid xs x ys: element column / row of every
+        target line (``x2xi``, SEM.py:23-36) and the Lagrange basis values there (GLL.py:105-116): (mx, Sx, ny, Sy)."""
+        from . import SEM
+        tabs = []
+        for pts, h, nel in ((xs, self.dx, self.N_ex), (ys, self.dy, self.N_ey)):
+            e, xi = SEM.x2xi(np.asarray(pts, dtype=np.float64).ravel(), h)
+            e = np.clip(e, 0, nel - 1)
+            S = GLL.standard_evaluation_matrix(self.P, xi)
+            tabs += [torch.from_numpy(e.astype(np.int32)).to(self.tdev), torch.from_numpy(np.ascontiguousarray(S)).to(self.tdev)]
+        return tuple(tabs)
 
     # ---- fast-diagonalisation plans (sem_ctx_set_fdm) ----------------------------------------------------------------------
     _EIG_HOST_MAX = 2100     # pencils up to this size are diagonalised on the host (LAPACK), larger ones with torch on the GPU

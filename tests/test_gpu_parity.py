@@ -362,6 +362,32 @@ def test_boussinesq_run_and_mesh_transfer(sem, golden):
     assert abs(up.max() * 1e3 * 0.71 - float(g["umax_RePr"])) < 1e-5
     Tp2, up2, vp2 = bsc.run((xp, yp), 1., 1., mode='GS', P_cd=4, N_ex_cd=4, N_ey_cd=4)
     assert abs(up2.max() * 1e3 * 0.71 - 3.649) < 2e-2 and np.abs(Tp2 - Tp).max() < 1e-2
+    # the same two-mesh problem through the device-resident Newton-Krylov coupling: same fixed point as block Gauss-Seidel
+    Tp3, up3, vp3 = bsc.run((xp, yp), 1., 1., mode='JNK', P_cd=4, N_ex_cd=4, N_ey_cd=4)
+    assert np.abs(Tp3 - Tp2).max() < 1e-7 and np.abs(up3 - up2).max() < 1e-7
+
+
+def test_coupled_device_operator_and_solve(sem):
+    """the coupled Jacobian-vector product and the GMRES + block-Jacobi solve of the Newton-Krylov coupling on the
+    device (sem_coupled_jvp / sem_coupled_solve) against the host-vector path that calls the two solvers method by method
+    (apply_linear / solve_linear semantics of OpenMDAO/*_Component.py), on DIFFERENT meshes for the two physics (the study's
+    N_e / 2 rule) so that the mesh-to-mesh transfer kernels are part of the operator."""
+    import ctypes as C
+    import torch
+    from sem_b200 import Boussinesq_SequentialCoupler as bsc
+    from sem_b200 import _lib as L
+    Re, Ra, Pr = 100.0, 500.0, 0.71
+    cd = sem.ConvectionDiffusionSolver(1., 1., Re * Pr, 4, 3, 3, T_W=0.5, T_E=-0.5, mtol=1e-13)
+    ns = sem.NavierStokesSolver(1., 1., Re, Ra / Pr, 4, 6, 6, mtol=1e-13, mtol_newton=1e-13, iprint=[])
+    sys_ = bsc._Coupled(cd, ns)
+    rng = np.random.default_rng(2)
+    x = 0.1 * rng.standard_normal(cd.N + 3 * ns.N)
+    r = sys_.residual(x)
+    sys_.linearize(x)
+    dx_host, its_host = bsc._gmres(sys_.jvp, sys_.block_jacobi, -r, 1e-11, 20, 500)
+    dx_dev, its_dev = sys_.device_solve(-r, 1e-11, 20, 500)
+    assert relerr(dx_dev, dx_host) < 1e-8 and abs(its_dev - its_host) <= 2
+    assert np.linalg.norm(sys_.jvp(dx_dev) + r) <= 2e-11
 
 
 def test_interpolation_device_matches_host(sem):
