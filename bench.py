@@ -193,16 +193,25 @@ def run_ours(args):
 
     for _ in range(warmup):
         step()
-    sync_all()
+    # the clock sampler (NVML, rank 0 only) starts BEFORE the barrier: started after it, rank 0 entered the timed region
+    # late and the other ranks' first exchange waited for it inside their timed region
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fused0 = lib.sem_ctx_partitioned_applies(d.ctx, 1)
+    if world > 1:
+        # the host barrier above releases the ranks up to ~100 us apart, which a 20-step region of ~0.1 ms steps does not
+        # amortise (every step waits for the neighbours): line the DEVICES up with an in-stream all-reduce right before
+        # the start event, so the timed region is K steps from a common start on every rank
+        dist.all_reduce(torch.zeros(1, device=d.tdev))
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     sync_all()
+    fused_steps = lib.sem_ctx_partitioned_applies(d.ctx, 1) - fused0
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=d.tdev, dtype=torch.float64)
@@ -297,8 +306,13 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(), "partition": f"{world} strips of element columns" if world > 1 else "none",
-                   "interface_exchange": {"p2p": "peer-memory mailboxes over NVLink (push kernel + epoch flag), no NCCL "
-                                                 "on the apply path", "nccl": "ncclSend/ncclRecv", "none": "none"}[d.comm_mode],
+                   "interface_exchange": {"p2p": ("inside the operator kernel: edge CTAs store their segments of the interface "
+                                                  "lines into the neighbour's mailbox over NVLink (per-strip epoch flags) "
+                                                  "and add what arrived; one launch per apply, no NCCL on the apply path"
+                                                  if fused_steps == steps else
+                                                  "peer-memory mailboxes over NVLink (push kernel + epoch flag), no NCCL "
+                                                  "on the apply path"),
+                                          "nccl": "ncclSend/ncclRecv", "none": "none"}[d.comm_mode],
                    "l2": "inputs larger than L2 (3 x 537 MB read per step)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "sem_march3_kernel<8, MODE_CD, false>", "peak_source": peak_src,
@@ -309,7 +323,9 @@ def run_ours(args):
                 "pageable_input": {"value": n_global / e2e_pageable_s / 1e9, "ms_per_step": e2e_pageable_s * 1e3,
                                    "note": "same call with an ordinary numpy array (what OpenMDAO passes); result still lands "
                                            "in a recycled page-locked block"}},
-        "gpu_launches": steps,
+        # one operator kernel per step; a partitioned apply that does not take the one-launch path is left edge + right edge +
+        # interior + exchange kernel (replayed as one CUDA graph)
+        "gpu_launches": steps if (world == 1 or fused_steps == steps) else 4 * steps,
         "clocks": clocks,
     }
     if parity is not None:

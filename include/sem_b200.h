@@ -145,6 +145,15 @@ int sem_ctx_set_ns_schur(sem_ctx *ctx, const sem_ns_schur_desc *desc);
 int sem_nccl_unique_id(unsigned char *out128);
 int sem_ctx_attach_comm(sem_ctx *ctx, const unsigned char *id128, int rank, int world);
 int sem_ctx_comm_mode(const sem_ctx *ctx);
+/* Operator applies without a post-operator (K, G, DIV, CD) on the peer-memory path are ONE kernel launch: the CTAs that
+ * finish an interface line store their segment of it straight into the neighbour's mailbox (per-strip epoch flags) and add
+ * the neighbour's contribution at the end of their chunk (SEM_B200_FUSED_XCH=0: the three-launch path + exchange kernel).
+ * sem_ctx_attach_loopback: one-GPU self-test of these paths -- the context must be an inner slab (0 < m_begin,
+ * m_end < N_ex); it becomes its own left and right neighbour, so line 0 and the last line are exchanged with each other. */
+int sem_ctx_attach_loopback(sem_ctx *ctx);
+/* partitioned operator applies issued so far: fused != 0 -> as one launch with the in-kernel exchange, else as edge /
+ * interior launches + exchange kernel */
+long long sem_ctx_partitioned_applies(const sem_ctx *ctx, int fused);
 
 /* ---- host <-> device packing of the reference's dense vectors (the numpy <-> device boundary) ----------------- */
 int sem_h2d(sem_ctx *ctx, const double *host_local, double *vec, void *stream);

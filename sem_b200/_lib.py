@@ -83,6 +83,8 @@ SIGNATURES = {
     "sem_nccl_unique_id": (C.c_int, [_P]),
     "sem_ctx_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "sem_ctx_comm_mode": (C.c_int, [_P]),
+    "sem_ctx_attach_loopback": (C.c_int, [_P]),
+    "sem_ctx_partitioned_applies": (_LL, [_P, C.c_int]),
     "sem_h2d": (C.c_int, [_P, _P, _P, _P]),
     "sem_d2h": (C.c_int, [_P, _P, _P, _P]),
     "sem_apply_stiffness": (C.c_int, [_P, _P, _P, _P]),

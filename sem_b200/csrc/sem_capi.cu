@@ -59,6 +59,7 @@ struct sem_ctx {
     cudaEvent_t ev_ring[SEM_GMRES_LAG];
     Comm comm;               // NCCL communicator of the element-column partition (has_comm)
     int has_comm;
+    long long n_fused, n_split;   // partitioned applies so far: one-launch (in-kernel exchange) / three launches + exchange kernel
     cudaStream_t s_side;     // low-priority stream: the interior of an operator runs here while the interface lines travel
     cudaStream_t s_side2;    // second side stream: right edge and interior run concurrently on small slabs
     cudaEvent_t ev_in, ev_edge, ev_side;
@@ -247,6 +248,22 @@ extern "C" int sem_ctx_attach_comm(sem_ctx* c, const unsigned char* id128, int r
     return 0;
 }
 
+// One-GPU self-test of the peer-memory exchange paths: the context must describe an inner slab (m_begin > 0, m_end < N_ex);
+// its two interface lines are then exchanged with each other through the context's own mailbox.
+extern "C" int sem_ctx_attach_loopback(sem_ctx* c) {
+    SEM_CHECK_CTX(c);
+    if (c->has_comm) { set_error("sem_ctx_attach_loopback: communicator already attached"); return -2; }
+    if (!c->g.has_left || !c->g.has_right) { set_error("sem_ctx_attach_loopback: the context must be an inner slab"); return -2; }
+    if (comm_init_loopback(c->comm, c->g.NY)) return -1;
+    c->has_comm = 1;
+    return 0;
+}
+
+extern "C" long long sem_ctx_partitioned_applies(const sem_ctx* c, int fused) {
+    if (!c) return -1;
+    return fused ? c->n_fused : c->n_split;
+}
+
 extern "C" int sem_ctx_comm_mode(const sem_ctx* c) {
     if (!c || !c->has_comm) return 0;
     return c->comm.p2p ? 2 : 1;
@@ -328,6 +345,49 @@ static int march(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st, int m_lo =
         q = march_geometry(c->g, q.Ty / 2 > 0 ? q.Ty / 2 : 1, c->Mx_req, c->sm_count, m_lo, m_hi);
     }
     return g_orders[c->g.P - 1].launch(mode, c->g, A, q, st);
+}
+
+// The whole partitioned apply as ONE launch (no post-operator, peer-memory mailboxes, v3 kernel): the chunks that finish the
+// interface lines come first in the grid (two element columns each: a priming phase and two marching steps), push their
+// segments of those lines into the neighbours' mailboxes when their chunk is done, and then add the neighbour's
+// contribution, which its own edge CTAs -- first in its grid too -- have normally delivered by then.  Every
+// push of a CTA precedes its waits and a pushing CTA waits for nothing, so the scheme cannot deadlock as long as the edge
+// CTAs of a launch are co-resident (checked: 2 x strips <= half the resident slots; else the three-launch path is used).
+// SEM_B200_FUSED_XCH=0 switches the path off for A/B runs.
+static const bool SEM_FUSED_XCH = [] {
+    const char* e = std::getenv("SEM_B200_FUSED_XCH");
+    return !(e && e[0] == '0');
+}();
+
+static bool fused_apply_possible(const sem_ctx* c, int mode, int n_fields) {
+    if (!SEM_FUSED_XCH || !c->has_comm || !c->comm.p2p || march_generation() != 3 || mode == MODE_NS) return false;
+    if (n_fields < 1 || n_fields > c->comm.max_fields) return false;
+    const auto& ord = g_orders[c->g.P - 1];
+    const MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm, 0, c->g.nex);
+    const int strips = (int)q.grid.x;
+    int resident = (int)((size_t)c->smem_sm / (ord.smem3(mode) + 1024));
+    if (resident > 32) resident = 32;
+    if (4 * strips > c->sm_count * resident) return false;
+    const int er = c->g.has_right ? 2 : 0, el = c->g.has_left ? 2 : 0;
+    return el + er < c->g.nex;   // there is an interior
+}
+
+static int fused_apply(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
+    A.zero = 0;
+    const auto& ord = g_orders[c->g.P - 1];
+    const int nex = c->g.nex;
+    MarchGeom q = march3_geometry(c->g, mode, c->Mx_req, c->sm_count, ord.smem3(mode), (size_t)c->smem_sm, 0, nex);
+    XchArgs X;
+    if (comm_fill_xch(c->comm, c->g, X)) return -1;
+    const int el = c->g.has_left ? 2 : 0, er = c->g.has_right ? 2 : 0;
+    if (el) { X.e_lo[X.nedge] = 0; X.e_hi[X.nedge] = el; X.nedge++; }
+    if (er) { X.e_lo[X.nedge] = nex - er; X.e_hi[X.nedge] = nex; X.nedge++; }
+    q.m_lo = el;
+    q.m_hi = nex - er;
+    q.grid.y = (unsigned)(X.nedge + (q.m_hi - q.m_lo + q.Mx - 1) / q.Mx);
+    q.xch = &X;
+    c->n_fused++;
+    return ord.launch3(mode, c->g, A, q, st);
 }
 
 static int ensure_streams(sem_ctx* c) {
@@ -421,6 +481,7 @@ static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializ
     int n = 0;
     for (double* p : fields)
         if (p) f[n++] = p;
+    if (!post && fused_apply_possible(c, mode, n)) return fused_apply(c, mode, A, st);   // the fields ARE the kernel's non-null outputs
     const int nex = c->g.nex;
     const int el = c->g.has_left ? std::min(SEM_EDGE_COLUMNS, nex) : 0;
     const int er = c->g.has_right ? std::min(SEM_EDGE_COLUMNS, nex - el) : 0;
@@ -430,6 +491,7 @@ static int apply_and_exchange(sem_ctx* c, int mode, MarchArgs& A, std::initializ
         return n ? comm_exchange_add(c->comm, c->g, f, n, st) : 0;
     }
     if (ensure_streams(c)) return -1;
+    c->n_split++;
     static const bool no_graph = std::getenv("SEM_B200_NO_GRAPH") != nullptr;
     if (no_graph) return partitioned_apply(c, mode, A, f, n, el, er, st, post);
 

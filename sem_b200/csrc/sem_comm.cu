@@ -1,4 +1,5 @@
 #include "sem_comm.cuh"
+#include "sem_tma.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -85,14 +86,63 @@ static inline unsigned long long* box_word(const Comm& c, void* box, int kind, i
     return w + ((size_t)kind * 2 + side) * c.max_fields + f;
 }
 
+// total bytes of a mailbox; fixes slot_len and the offset of the fused-exchange region
+static size_t box_layout(Comm& c, int NY) {
+    c.slot_len = ((size_t)NY + 15) & ~(size_t)15;
+    const size_t legacy = box_data_doubles(c) * sizeof(double) + (size_t)3 * 2 * c.max_fields * sizeof(unsigned long long);
+    c.fused_off = (legacy + 127) & ~(size_t)127;
+    const size_t fused = box_data_doubles(c) * sizeof(double) + (size_t)2 * 2 * c.max_fields * c.slot_len * sizeof(unsigned long long);
+    return c.fused_off + fused;
+}
+static inline double* fused_slot(const Comm& c, void* box, int side) {   // parity 0, field 0
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(box) + c.fused_off) + (size_t)side * c.max_fields * c.slot_len;
+}
+static inline unsigned long long* fused_word(const Comm& c, void* box, int kind, int side) {   // kind 0: arrived, 1: epoch; field 0
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(reinterpret_cast<char*>(box) + c.fused_off) +
+                                                                  box_data_doubles(c));
+    return w + ((size_t)kind * 2 + side) * c.max_fields * c.slot_len;
+}
+
+int comm_fill_xch(const Comm& c, const MeshDev& g, XchArgs& X) {
+    std::memset(&X, 0, sizeof(X));
+    if (!c.p2p) { set_error("comm_fill_xch: no peer-memory mailboxes"); return -2; }
+    X.mask = (g.has_left ? 1 : 0) | (g.has_right ? 2 : 0);
+    X.slot_len = c.slot_len;
+    X.parity_stride = (unsigned long long)2 * c.max_fields * c.slot_len;
+    X.flag_stride = c.slot_len;
+    for (int s = 0; s < 2; ++s) {
+        if (!(X.mask & (1 << s))) continue;
+        // my line 0 is the left neighbour's last line (its side 1); my last line is the right neighbour's line 0 (its side 0)
+        X.peer_slot[s] = fused_slot(c, c.peer_box[s], 1 - s);
+        X.peer_flag[s] = fused_word(c, c.peer_box[s], 0, 1 - s);
+        X.my_slot[s] = fused_slot(c, c.box, s);
+        X.my_flag[s] = fused_word(c, c.box, 0, s);
+        X.epoch[s] = fused_word(c, c.box, 1, s);
+    }
+    return 0;
+}
+
+int comm_init_loopback(Comm& c, int NY) {
+    std::memset(&c, 0, sizeof(c));
+    c.rank = 0;
+    c.world = 1;
+    c.max_fields = 4;
+    c.loopback = 1;
+    const size_t bytes = box_layout(c, NY);
+    SEM_CUDA(cudaMalloc(&c.box, bytes));
+    SEM_CUDA(cudaMemset(c.box, 0, bytes));
+    c.peer_box[0] = c.peer_box[1] = c.box;
+    c.p2p = 1;
+    return 0;
+}
+
 // Allocate the mailbox, spread its IPC handle (ncclAllGather of the 64 handle bytes), map the neighbours' mailboxes.
 // All ranks agree on the outcome (all-reduce of a success count): either every rank pushes or every rank uses NCCL.
 static int p2p_init(Comm& c, int NY) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
     const bool off = std::getenv("SEM_B200_NO_P2P") != nullptr;
     ncclComm_t comm = (ncclComm_t)c.nccl;
-    c.slot_len = ((size_t)NY + 15) & ~(size_t)15;
-    const size_t bytes = box_data_doubles(c) * sizeof(double) + (size_t)3 * 2 * c.max_fields * sizeof(unsigned long long);
+    const size_t bytes = box_layout(c, NY);
     int ok = off ? 0 : 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
@@ -158,8 +208,10 @@ int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY
 }
 
 void comm_destroy(Comm& c) {
-    for (int s = 0; s < 2; ++s)
-        if (c.peer_box[s]) { cudaIpcCloseMemHandle(c.peer_box[s]); c.peer_box[s] = nullptr; }
+    for (int s = 0; s < 2; ++s) {
+        if (c.peer_box[s] && !c.loopback) cudaIpcCloseMemHandle(c.peer_box[s]);
+        c.peer_box[s] = nullptr;
+    }
     if (c.nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl);
     if (c.recv) cudaFree(c.recv);
     if (c.box) cudaFree(c.box);
@@ -170,16 +222,19 @@ void comm_destroy(Comm& c) {
 }
 
 int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st) {
+    if (c.loopback) return 0;   // one rank: the sum is the buffer itself
     SEM_NCCL(g_nccl.AllReduce(buf, buf, (size_t)k, ncclDouble, ncclSum, (ncclComm_t)c.nccl, st));
     return 0;
 }
 
 int comm_reduce_scatter_sum(const Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t st) {
+    if (c.loopback) { SEM_CUDA(cudaMemcpyAsync(recv, send, count_per_rank * sizeof(double), cudaMemcpyDeviceToDevice, st)); return 0; }
     SEM_NCCL(g_nccl.ReduceScatter(send, recv, count_per_rank, ncclDouble, ncclSum, (ncclComm_t)c.nccl, st));
     return 0;
 }
 
 int comm_allgather(const Comm& c, const double* send, double* recv, size_t count_per_rank, cudaStream_t st) {
+    if (c.loopback) { if (recv != send) SEM_CUDA(cudaMemcpyAsync(recv, send, count_per_rank * sizeof(double), cudaMemcpyDeviceToDevice, st)); return 0; }
     SEM_NCCL(g_nccl.AllGather(send, recv, count_per_rank, ncclDouble, (ncclComm_t)c.nccl, st));
     return 0;
 }
@@ -221,14 +276,6 @@ struct WaitAddArgs {
     int n;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // one CTA per interface line: store it into the neighbour's mailbox (NVLink stores), then release the epoch flag there
 __global__ void __launch_bounds__(1024) k_halo_push(const PushArgs p, int NY) {

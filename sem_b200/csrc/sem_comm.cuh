@@ -24,10 +24,21 @@ struct Comm {
                                      // 64-bit words: arrived[2][max_fields] (written by the neighbours),
                                      // sent[2][max_fields], consumed[2][max_fields] (local epoch counters)
     void* peer_box[2];               // the left / right neighbour's mailbox mapped into this process (or null)
+    // Second region of the same mailbox, used by the exchange that is fused into the operator kernel (XchArgs,
+    // sem_march3_kernel): its own data slots [2 parities][2 sides][max_fields][slot_len] and per-STRIP flag words
+    // arrived[2 sides][max_fields][slot_len], epoch[2 sides][max_fields][slot_len], so that its epochs never share a
+    // parity slot with the per-line epochs of the stand-alone exchange kernels.
+    size_t fused_off;                // byte offset of that region in a mailbox
+    int loopback;                    // self-test on one GPU: this rank is its own left and right neighbour (no NCCL)
 };
 
 int comm_unique_id(unsigned char out[128]);
 int comm_init(Comm& c, const unsigned char id[128], int rank, int world, int NY);
+// One-GPU self-test of the peer-memory paths: a communicator whose left and right neighbour are this rank itself, so the
+// interface lines of a slab context (has_left / has_right) are exchanged with each other (line 0 <-> last line).
+int comm_init_loopback(Comm& c, int NY);
+// arguments of the in-kernel exchange for this rank's slab (peer-memory path only)
+int comm_fill_xch(const Comm& c, const MeshDev& g, XchArgs& X);
 void comm_destroy(Comm& c);
 // in-place sum of k doubles over all ranks
 int comm_allreduce_sum(const Comm& c, double* buf, int k, cudaStream_t st);

@@ -86,6 +86,24 @@ struct MarchArgs {
     BCSpec bc;
 };
 
+// In-kernel interface exchange of a partitioned apply (sem_march3_kernel; peer-memory mailboxes, see sem_comm.cuh).
+// mask == 0: none.  The strips that finish an interface line store their segment of it straight into the neighbour's
+// mailbox over NVLink and release a per-strip epoch flag there; at the end of its chunk the same CTA acquires the
+// neighbour's flag for the same segment and adds what arrived.  Index [0]: local line 0 (left neighbour), [1]: last line.
+struct XchArgs {
+    int mask;                          // bit 0: line 0 is exchanged, bit 1: the last line
+    int nedge;                         // the first `nedge` values of blockIdx.y are the edge chunks below
+    int e_lo[2], e_hi[2];              // element columns [e_lo, e_hi) of the edge chunks
+    unsigned long long slot_len;       // doubles between the fields of a mailbox slot
+    unsigned long long parity_stride;  // doubles between the two epoch parities
+    unsigned long long flag_stride;    // 64-bit words between the fields of a flag array
+    double* peer_slot[2];              // parity 0, field 0 of the slot this rank writes in the neighbour's mailbox
+    unsigned long long* peer_flag[2];  // the neighbour's arrival flags of that slot [field][strip]
+    const double* my_slot[2];          // the slot the neighbour writes in this rank's mailbox
+    unsigned long long* my_flag[2];    // this rank's arrival flags [field][strip]
+    unsigned long long* epoch[2];      // local epoch counters [field][strip] (device memory: graph-replayable)
+};
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace semb

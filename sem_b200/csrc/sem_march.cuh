@@ -476,6 +476,7 @@ struct MarchGeom {
     int Ty, Mx, pitch, threads;
     int m_lo = 0, m_hi = 0;   // element columns covered by the launch
     dim3 grid;
+    const XchArgs* xch = nullptr;   // v3 only: in-kernel interface exchange (fused partitioned apply)
 };
 
 inline MarchGeom march_geometry(const MeshDev& g, int Ty_req, int Mx_req, int sm_count, int m_lo, int m_hi) {

@@ -549,11 +549,64 @@ struct March3 {
             if (fix) bc_fixup(g, A, m, iy0, c0, own[0], own[NC - 1], sB, &aprev[0][0]);
         }
     }
+
+    // ---- in-kernel interface exchange (partitioned apply, XchArgs) -----------------------------------------------------------
+    // Called once, at the end of a chunk that holds an interface line (side 0: local line 0, side 1: the last line).  The strip
+    // stores its segment of the line into the neighbour's mailbox (every lane re-reads what it stored itself: finalize_* and
+    // bc_fixup write a node from the same lane, program order) and releases the strip's epoch flag there; then it acquires the
+    // neighbour's flag for the same segment and adds what arrived (lower rank's partial sum first).  Every push precedes every
+    // wait.  Not inlined on purpose: compiled into the kernel body it raised the uniform-register pressure of the marching
+    // loop and ptxas demoted the table offset to a vector register -- every table fetch an LDC instead of an LDCU, the
+    // slab apply 18 % slower.
+    static __device__ __noinline__ void xch_exchange(const MeshDev& g, const MarchArgs& A, const XchArgs& X, bool first, bool last,
+                                                     int iy0, bool own0, bool own1) {
+        double* const y[3] = {A.y0, A.y1, A.y2};
+        const int strip = blockIdx.x;
+        const bool own[2] = {own0, own1};
+        for (int pass = 0; pass < 2; ++pass) {            // 0: push, 1: wait + add
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? first : last)) continue;
+                const size_t ix = side == 0 ? 0 : (size_t)g.nex * P;
+                int fo = 0;
+                for (int o = 0; o < NOUT; ++o) {
+                    if (!y[o]) continue;
+                    unsigned long long* ep = X.epoch[side] + fo * X.flag_stride + strip;
+                    const unsigned long long e = *ep + 1ull;
+                    double* line = y[o] + ix * g.LD + iy0;
+                    if (pass == 0) {
+                        double* dst = X.peer_slot[side] + (e & 1ull) * X.parity_stride + fo * X.slot_len + iy0;
+                        for (int c = 0; c < NC; ++c)
+                            if (own[c]) dst[c] = line[c];
+                        __threadfence_system();
+                        __syncwarp();
+                        if (threadIdx.x == 0) st_release_sys(X.peer_flag[side] + fo * X.flag_stride + strip, e);
+                    } else {
+                        if (threadIdx.x == 0) wait_epoch(X.my_flag[side] + fo * X.flag_stride + strip, e);
+                        __syncwarp();
+                        const double* recv = X.my_slot[side] + (e & 1ull) * X.parity_stride + fo * X.slot_len + iy0;
+                        for (int c = 0; c < NC; ++c)
+                            if (own[c]) {
+                                const double mine = line[c], other = __ldcg(recv + c);   // written by a peer: read it from L2
+                                line[c] = side == 0 ? (other + mine) : (mine + other);
+                            }
+                        __syncwarp();
+                        if (threadIdx.x == 0) *ep = e;
+                    }
+                    ++fo;
+                }
+            }
+        }
+    }
 };
 
-template <int P, int MODE, bool PW>
+// XCH: the fused partitioned apply (in-kernel interface exchange after the march, edge chunks first).  A template flag and
+// not a run-time test of X.mask, and nothing of it inside the marching loop: with a test and the push of line 0 compiled into
+// the loop of the one-GPU kernel ptxas scheduled the CD apply differently (164 instead of 184 registers) and config 5 ran
+// 4 % slower (0.856 against 0.895 of the HBM roofline).
+template <int P, int MODE, bool PW, bool XCH = false>
 __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ MeshDev g, const __grid_constant__ MarchArgs A,
-                                                        const int Mx, const int m_lo, const int m_hi) {
+                                                        const __grid_constant__ XchArgs X, const int Mx, const int m_lo,
+                                                        const int m_hi) {
     using M3 = March3<P, MODE, PW>;
     using GE = March3Geom<P, MODE>;
     constexpr int NF = M3::NF, NACC = M3::NACC, NOUT = M3::NOUT, NSTG = M3::NSTG, NC = M3::NC, NL = M3::NL, G = M3::G;
@@ -569,8 +622,19 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     const int n0 = blockIdx.x * EW;
     const int nty = max(0, min(EW, g.ney - n0));          // the last strip holds the remaining ney % EW rows (maybe none)
     const bool last_strip = (blockIdx.x == gridDim.x - 1);
-    const int m0 = m_lo + blockIdx.y * Mx;              // the launch covers the element columns m_lo .. m_hi - 1
-    const int m1 = min(m0 + Mx, m_hi);
+    // the launch covers the element columns m_lo .. m_hi - 1 in chunks of Mx; a fused partitioned apply puts the chunks
+    // that finish the interface lines first (lowest blockIdx.y = scheduled first), the interior chunks after them
+    int m0 = m_lo + blockIdx.y * Mx, m1 = min(m0 + Mx, m_hi);
+    if constexpr (XCH) {
+        // selects on uniform values with static indices: a branch or an indexed read of the parameter array yields per-thread
+        // registers, and the table offset z = m >> 30 derived from them turns every table fetch from LDCU into LDC (ADU
+        // pipe; measured: 18 % slower)
+        const int by = blockIdx.y;
+        const int e0 = by == 0 ? X.e_lo[0] : X.e_lo[1], e1 = by == 0 ? X.e_hi[0] : X.e_hi[1];
+        const int i0 = m_lo + (by - X.nedge) * Mx, i1 = min(i0 + Mx, m_hi);
+        m0 = by < X.nedge ? e0 : i0;
+        m1 = by < X.nedge ? e1 : i1;
+    }
     // y-halo: the P nodes below the strip, one more when the strip starts at an odd node (odd orders) so that the TMA
     // source address stays 16-byte aligned
     const int halo = (n0 > 0) ? P + ((n0 * P - P) & 1) : 0;
@@ -716,8 +780,16 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
 
     // ---- march --------------------------------------------------------------------------------------------------------------------
     uint32_t ph0 = 0, ph1 = 1;
-    for (int m = m0; m < m1; ++m) {
-        const int b = (m - m0) & 1;
+    // The table offset z (below) must stay on the uniform datapath.  Derived from m it does not always: ptxas keeps m in a
+    // vector register in many instantiations (every table fetch then is an LDC on the ADU pipe: P = 10 CD / NS, P = 12 and
+    // 16 CD, P = 8 NS residual, and every kernel whose m0 comes out of the selects of the XCH chunk mapping), so z comes
+    // from a second counter that starts at a constant.  Measured at 67 M nodes (CD, fraction of the HBM roofline): P = 10
+    // 54 -> 66 %, P = 12 38 -> 56 %, P = 16 28 -> 54 %; the one-GPU CD apply of the orders 4 .. 8, which was on LDCUs either
+    // way, keeps the derivation from m (P = 8: 89.3 % against 88.3 % with the second counter).
+    constexpr bool ZIT = XCH || !(MODE == MODE_CD && !PW && P >= 4 && P <= 8);
+    int it = 0;
+    for (int m = m0; m < m1; ++m, ++it) {
+        const int b = (ZIT ? it : m - m0) & 1;
         if constexpr (M3::NODE_FAST) {
             if (A.d0 && xthr) {
                 const double* const dp[4] = {A.d0, A.d1, A.d2, A.d3};
@@ -738,7 +810,7 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         for (int l = 0; l < NL; ++l) wx[l] = (m + 1 == g.nex) ? wx_end[l] : wx_in[l];
         // z == 0 (m < 2^30), but the compiler cannot prove it: uniform and different in every trip, so the constant-table
         // fetches stay LDCUs next to their DFMAs instead of being hoisted into ~100 registers (and R2UR'd back)
-        const int z = m >> 30;
+        const int z = (ZIT ? it : m) >> 30;
         M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, z);
         __syncwarp();
         if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
@@ -748,8 +820,13 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
 
     // ---- epilogue: the last line of the slab has no element to its right ---------------------------------------------------------
     if (xthr && m1 == g.nex) M3::finalize_slow(g, A, g.nex * P, iy0, own, xc, yc, a0, wyA);
-}
 
+    // ---- fused partitioned apply: exchange of the interface lines --------------------------------------------------------------
+    if constexpr (XCH) {
+        const bool first = (X.mask & 1) && blockIdx.y == 0, last = (X.mask & 2) && m1 == g.nex;   // edge chunk 0 starts at column 0
+        if (first || last) M3::xch_exchange(g, A, X, first, last, iy0, own[0], own[NC - 1]);
+    }
+}
 // host mirror of March3Traits: node columns per lane of a (P, mode)
 inline int march3_nc(int P, int mode) { return (mode != MODE_NS && P % 2 == 0 && P <= 10) ? 2 : 1; }
 

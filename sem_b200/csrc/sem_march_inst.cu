@@ -3,6 +3,7 @@
 #include "sem_march.cuh"
 #include "sem_march3.cuh"
 #include <cmath>
+#include <cstring>
 #include "sem_dispatch.h"
 
 #ifndef SEM_P
@@ -52,18 +53,32 @@ int SEM_CAT(march_launch_p, SEM_P)(int, const MeshDev&, const MarchArgs&, const 
 #endif
 
 // ---- v3 kernel (one warp per strip, TMA-staged, folded tables): every order, all modes.
-template <int P, int MODE, bool PW>
-static int launch_mode3(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
+template <int P, int MODE, bool PW, bool XCH>
+static int launch_mode3x(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
     constexpr size_t smem = March3Geom<P, MODE>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
         if (smem > 48 * 1024)
-            SEM_CUDA(cudaFuncSetAttribute(sem_march3_kernel<P, MODE, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SEM_CUDA(cudaFuncSetAttribute(sem_march3_kernel<P, MODE, PW, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    sem_march3_kernel<P, MODE, PW><<<q.grid, 32, smem, st>>>(g, A, q.Mx, q.m_lo, q.m_hi);
+    XchArgs X;
+    if (XCH) X = *q.xch;
+    else std::memset(&X, 0, sizeof(X));
+    sem_march3_kernel<P, MODE, PW, XCH><<<q.grid, 32, smem, st>>>(g, A, X, q.Mx, q.m_lo, q.m_hi);
     SEM_CUDA(cudaGetLastError());
     return 0;
+}
+
+// the fused partitioned apply (q.xch) exists for the modes without a post-operator: K, G, DIV, CD
+template <int P, int MODE, bool PW>
+static int launch_mode3(const MeshDev& g, const MarchArgs& A, const MarchGeom& q, cudaStream_t st) {
+    if constexpr (MODE != MODE_NS) {
+        if (q.xch) return launch_mode3x<P, MODE, PW, true>(g, A, q, st);
+    } else {
+        if (q.xch) { set_error("march3: no in-kernel exchange in the NS mode"); return -2; }
+    }
+    return launch_mode3x<P, MODE, PW, false>(g, A, q, st);
 }
 
 int SEM_CAT(march3_launch_p, SEM_P)(int mode, const MeshDev& g, const MarchArgs& A, const MarchGeom& q,

@@ -49,4 +49,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// system-scope release / acquire on a 64-bit flag word (peer memory over NVLink)
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= e; a neighbour that died makes the kernel trap after 120 s instead of hanging the box
+__device__ __forceinline__ void wait_epoch(const unsigned long long* flag, unsigned long long e) {
+    unsigned long long t0 = 0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(flag) < e) {
+        __nanosleep(64);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 120ull * 1000000000ull) __trap();
+    }
+}
+
 }  // namespace semb

@@ -158,6 +158,14 @@ def main():
         xp, yp = yp.mul_(s), xp
     check("40 chained partitioned K applies", relerr(dpar.to_host(xp), dpar.part.local_slice(dall.to_host(xs))), 1e-11)
 
+    # which partitioned-apply path ran: with peer-memory mailboxes the K / G / DIV / CD applies are one launch (in-kernel exchange)
+    nfused, nsplit = (int(dpar.lib.sem_ctx_partitioned_applies(dpar.ctx, k)) for k in (1, 0))
+    if rank == 0:
+        print(f"partitioned K applies: {nfused} one-launch, {nsplit} three-launch")
+    want_fused = dpar.comm_mode == "p2p" and os.environ.get("SEM_B200_FUSED_XCH", "1") != "0"
+    if want_fused != (nfused > 0) or (want_fused and nsplit > 0):
+        fails.append(f"rank {rank}: expected the {'one' if want_fused else 'three'}-launch path, counters {nfused}/{nsplit}")
+
     allf = [None] * world
     dist.all_gather_object(allf, fails)
     dist.destroy_process_group()

@@ -528,3 +528,23 @@ def T_last(g, mode, n):
         if str(g[f"{mode}/{i}/who"]) == "cd._get_interpol":
             return g[f"{mode}/{i}/arg0"]
     raise AssertionError("trace holds no cd._get_interpol call")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One-GPU self-test of the partitioned apply's peer-memory paths (sem_ctx_attach_loopback): an inner slab is its own left and
+# right neighbour, so its two interface lines are exchanged with each other.  Expected, bit for bit: the plain slab apply
+# (no communicator: partial sums on the interface lines) with line 0 and the last line both replaced by their sum.
+@pytest.mark.parametrize("P,nex,ney,expect_fused", [(8, 40, 24, True), (4, 64, 40, True), (5, 30, 7, True), (8, 3, 130, False)])
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_partitioned_apply_loopback_exchange(sem, P, nex, ney, expect_fused, fused):
+    import subprocess
+    import sys
+    if fused == "0":
+        # SEM_B200_FUSED_XCH is read once per process: the three-launch + exchange-kernel path runs in a child
+        env = dict(os.environ, SEM_B200_FUSED_XCH="0", SEM_LOOPBACK_CHILD=f"{P},{nex},{ney}")
+        r = subprocess.run([sys.executable, "-m", "tests.loopback_check"], env=env, capture_output=True, text=True,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+        assert r.returncode == 0 and "LOOPBACK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    from tests.loopback_check import check
+    check(sem, P, nex, ney, expect_fused=expect_fused)

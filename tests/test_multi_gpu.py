@@ -2,7 +2,8 @@
 diagonalisation, partitioned NS preconditioner) against the single-GPU path and the oracle.  Skipped when the box has fewer
 GPUs than ranks (the host-side logic is covered on CPU by tests/test_partition_gloo.py).  world = 3 exercises ranks with two
 neighbours and slabs of unequal width; the two environment variants cover the NCCL send/recv fallback of the interface
-exchange and the eager (no CUDA graph) path."""
+exchange, the eager (no CUDA graph) path and the three-launch + exchange-kernel path that the one-launch apply (exchange inside
+the operator kernel) replaced as the default."""
 import os
 import subprocess
 import sys
@@ -12,7 +13,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,env", [(2, {}), (2, {"SEM_B200_NO_P2P": "1"}), (2, {"SEM_B200_NO_GRAPH": "1"}), (3, {}), (4, {}),
+@pytest.mark.parametrize("world,env", [(2, {}), (2, {"SEM_B200_NO_P2P": "1"}), (2, {"SEM_B200_NO_GRAPH": "1"}), (2, {"SEM_B200_FUSED_XCH": "0"}),
+                                       (3, {}), (4, {}),
                                        (8, {})])
 def test_partitioned_path(world, env):
     import torch
