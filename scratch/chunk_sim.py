@@ -36,3 +36,23 @@ for c in np.arange(0.5, 4.01, 0.25):
     print(f'c={c:.2f} step={ts:.3f} us t0={t0:.2f} rms={err:.2f}')
     if best is None or err < best[0]: best = (err, c, ts, t0)
 print('best', best)
+
+# ---- tapered (guided) chunk sequences: next width = clamp(remaining / (W f)), W = slots / strips concurrent chunk columns
+def guided(ncol, W, f, lo, hi):
+    out, r = [], ncol
+    while r > 0:
+        w = int(max(lo, min(hi, math.ceil(r / (W * f)))))
+        w = min(w, r)
+        out.append(w); r -= w
+    return out
+err, c, ts, t0 = best
+for ncol in (124, 128, 256, 512, 1024):
+    u = {Mx: makespan(uniform(ncol, Mx), strips, slots, c) * ts + t0 for Mx in (4, 5, 6, 8, 10, 12, 14, 16)}
+    bu = min(u, key=u.get)
+    line = f'ncol={ncol}: best uniform Mx={bu} {u[bu]:.1f} us |'
+    for f in (1.0, 1.5, 2.0, 3.0):
+        for hi in (8, 12, 16, 24):
+            w = guided(ncol, slots / strips, f, 2, hi)
+            line += f' f={f} hi={hi}: {makespan(w, strips, slots, c) * ts + t0:.1f} ({len(w)})'
+        line += ' |'
+    print(line)

@@ -359,6 +359,8 @@ static const bool SEM_FUSED_XCH = [] {
     return !(e && e[0] == '0');
 }();
 
+static bool large_interior(const sem_ctx* c, int interior_columns);
+
 static bool fused_apply_possible(const sem_ctx* c, int mode, int n_fields) {
     if (!SEM_FUSED_XCH || !c->has_comm || !c->comm.p2p || march_generation() != 3 || mode == MODE_NS) return false;
     if (n_fields < 1 || n_fields > c->comm.max_fields) return false;
@@ -369,7 +371,18 @@ static bool fused_apply_possible(const sem_ctx* c, int mode, int n_fields) {
     if (resident > 32) resident = 32;
     if (4 * strips > c->sm_count * resident) return false;
     const int er = c->g.has_right ? 2 : 0, el = c->g.has_left ? 2 : 0;
-    return el + er < c->g.nex;   // there is an interior
+    if (el + er >= c->g.nex) return false;   // no interior
+    // A large interior (several resident rounds of CTAs) hides the whole exchange of the three-launch path, and the edge CTAs
+    // of the one-launch path then only lose time waiting for the neighbour while they hold 2 x strips resident slots:
+    // measured at 2 GPUs on config 5 (512-column slabs) 0.205 ms fused against 0.199 ms split; the 128-column slab of 8 GPUs
+    // takes 66.5 us fused against 71.3 us split (one-GPU loopback).  SEM_B200_FUSED_XCH=2 forces the one-launch path.
+    static const bool force = [] { const char* e = std::getenv("SEM_B200_FUSED_XCH"); return e && e[0] == '2'; }();
+    return force || !large_interior(c, c->g.nex - el - er);
+}
+
+static bool large_interior(const sem_ctx* c, int interior_columns) {
+    const long long interior_ctas = (long long)(c->g.ney / 8 + 1) * ((interior_columns + 15) / 16);
+    return interior_ctas >= 3ll * 6 * c->sm_count;
 }
 
 static int fused_apply(sem_ctx* c, int mode, MarchArgs& A, cudaStream_t st) {
@@ -439,8 +452,7 @@ static int partitioned_apply(sem_ctx* c, int mode, MarchArgs& A, double* const* 
     // A large interior (several resident rounds of one-warp CTAs) goes first: it starts at once, and the edge launches on
     // the higher-priority stream slip in as soon as its first CTAs retire -- long before it ends.  A small interior
     // (8 GPUs on config 5: about one round) would delay the edges past its own end, so there the edges go first.
-    const long long interior_ctas = (long long)(c->g.ney / 8 + 1) * ((nex - el - er + 15) / 16);
-    const bool interior_first = interior_ctas >= 3ll * 6 * c->sm_count;
+    const bool interior_first = large_interior(c, nex - el - er);
     if (interior_first) {
         if (march(c, mode, A, c->s_side, el, nex - er)) return -1;
         SEM_CUDA(cudaEventRecord(c->ev_side, c->s_side));

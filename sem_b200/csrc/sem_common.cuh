@@ -104,6 +104,13 @@ struct XchArgs {
     unsigned long long* epoch[2];      // local epoch counters [field][strip] (device memory: graph-replayable)
 };
 
+// 2-D TMA tensor maps of the staged fields of a marching launch (opaque 128-byte CUtensorMap objects, encoded on the host:
+// sem_tmap.cu).  Field = [NX][LD] doubles, box = [P lines][PITCH columns]: one cp.async.bulk.tensor.2d per field and step.
+struct alignas(64) TMap { unsigned long long opaque[16]; };
+struct TmaMaps { TMap m[5]; };
+// encode (or fetch from a small cache) the tensor map of a field for a box of box_cols x box_lines doubles
+int tmap_get(const double* base, const MeshDev& g, int box_cols, int box_lines, TMap* out);
+
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace semb

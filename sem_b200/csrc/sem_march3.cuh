@@ -78,6 +78,9 @@ struct March3Geom {
     static constexpr int NSTG = TR::NF + 2 * TR::NV;                     // staged fields: contracted, then U, then V
     static constexpr int SMEM_DOUBLES = (2 * NSTG + TR::NACC) * P * PITCH + TR::NACC * P * TPW;
     static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 16;
+    // One 2-D tensor-map copy per field and step (box = P lines x PITCH columns, which lands with exactly the row pitch of the
+    // tile) when every field's stage starts 128-byte aligned; otherwise P one-line bulk copies per field (16-byte alignment).
+    static constexpr bool TMA2D = (P * PITCH) % 16 == 0;
     static_assert(EW * P / NC <= 32 && (P / NL) * EW <= 32, "a strip must fit one warp in both phases");
 };
 
@@ -605,14 +608,14 @@ struct March3 {
 // 4 % slower (0.856 against 0.895 of the HBM roofline).
 template <int P, int MODE, bool PW, bool XCH = false>
 __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ MeshDev g, const __grid_constant__ MarchArgs A,
-                                                        const __grid_constant__ XchArgs X, const int Mx, const int m_lo,
-                                                        const int m_hi) {
+                                                        const __grid_constant__ XchArgs X, const __grid_constant__ TmaMaps TM,
+                                                        const int Mx, const int m_lo, const int m_hi) {
     using M3 = March3<P, MODE, PW>;
     using GE = March3Geom<P, MODE>;
     constexpr int NF = M3::NF, NACC = M3::NACC, NOUT = M3::NOUT, NSTG = M3::NSTG, NC = M3::NC, NL = M3::NL, G = M3::G;
     constexpr int EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW;
     constexpr int STAGE = NSTG * P * PITCH;               // doubles per stage
-    extern __shared__ __align__(16) double smem3[];
+    extern __shared__ __align__(128) double smem3[];
     double* sS = smem3;                                   // [2][NSTG][P][PITCH] staged node lines (TMA destination)
     double* sA = sS + 2 * STAGE;                          // [NACC][P][PITCH]    y-part rows 0..P-1 of every element line
     double* sT = sA + NACC * P * PITCH;                   // [NACC][P][TPW]      y-part row P (node shared with the element above)
@@ -693,14 +696,23 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     // one elected lane issues the bulk copies of node lines line_first .. line_first + nlines - 1 of every staged field into slots
     // slot_first .. of buffer `buf`.  (One copy per lane does not parallelise: UBLKCP is a uniform-datapath instruction
     // and the compiler serialises the lanes with an ELECT loop, ~10 instructions per copy.)
+    // With tensor maps (GE::TMA2D) the same call is ONE copy per field: the box of P lines x PITCH columns whose slot
+    // `slot_first` is line `line_first`; lines before line 0 (the one-line call of the prologue) arrive as zeros.
     auto issue = [&](int buf, int line_first, int nlines, int slot_first) {
         if (elect_one()) {
-            mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
+            if constexpr (GE::TMA2D) {
+                mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * P * PITCH * 8));
 #pragma unroll
-            for (int f = 0; f < NSTG; ++f) {
-                const double* src = field(f) + (size_t)line_first * g.LD + ybase;
-                double* dst = sS + buf * STAGE + (f * P + slot_first) * PITCH;
-                for (int k = 0; k < nlines; ++k) bulk_g2s(dst + k * PITCH, src + (size_t)k * g.LD, line_bytes, &bar[buf]);
+                for (int f = 0; f < NSTG; ++f)
+                    tma_load_2d(sS + buf * STAGE + f * P * PITCH, &TM.m[f], ybase, line_first - slot_first, &bar[buf]);
+            } else {
+                mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
+#pragma unroll
+                for (int f = 0; f < NSTG; ++f) {
+                    const double* src = field(f) + (size_t)line_first * g.LD + ybase;
+                    double* dst = sS + buf * STAGE + (f * P + slot_first) * PITCH;
+                    for (int k = 0; k < nlines; ++k) bulk_g2s(dst + k * PITCH, src + (size_t)k * g.LD, line_bytes, &bar[buf]);
+                }
             }
         }
         __syncwarp();
@@ -747,12 +759,11 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         for (int l = 0; l < NL; ++l) wx[l] = 0.5 * g.dx * asm_weight<P>(ix - P + 1 + sp + l * G, g.nex);
         mbar_wait(&bar[1], 0);
         const double* sB = sS + STAGE;
-        M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, m0 >> 30);
+        M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, 0);
         __syncwarp();
         if (xthr) {
             if (m0 > 0) {
-                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd,
-                                           m0 >> 30);
+                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, 0);
             } else {
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {

@@ -65,7 +65,15 @@ static int launch_mode3x(const MeshDev& g, const MarchArgs& A, const MarchGeom& 
     XchArgs X;
     if (XCH) X = *q.xch;
     else std::memset(&X, 0, sizeof(X));
-    sem_march3_kernel<P, MODE, PW, XCH><<<q.grid, 32, smem, st>>>(g, A, X, q.Mx, q.m_lo, q.m_hi);
+    TmaMaps TM;
+    if constexpr (March3Geom<P, MODE>::TMA2D) {
+        using TR = ModeTraits<MODE>;
+        const double* f[5] = {A.a, TR::NF > 1 ? A.b : nullptr, TR::NF > 2 ? A.c : nullptr, nullptr, nullptr};
+        if (TR::NV) { f[TR::NF] = A.U; f[TR::NF + 1] = A.V; }
+        for (int k = 0; k < March3Geom<P, MODE>::NSTG; ++k)
+            if (tmap_get(f[k], g, March3Geom<P, MODE>::PITCH, P, &TM.m[k])) return -1;
+    }
+    sem_march3_kernel<P, MODE, PW, XCH><<<q.grid, 32, smem, st>>>(g, A, X, TM, q.Mx, q.m_lo, q.m_hi);
     SEM_CUDA(cudaGetLastError());
     return 0;
 }
