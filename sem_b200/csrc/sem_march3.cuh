@@ -621,6 +621,10 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     double* sT = sA + NACC * P * PITCH;                   // [NACC][P][TPW]      y-part row P (node shared with the element above)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sT + NACC * P * TPW);   // [2]
 
+    // back-to-back applies: the next launch may place its CTAs as soon as all of ours have started, i.e. into the slots our
+    // tail frees; its set-up (barriers, accumulator clear, weights) then overlaps our tail and its first loads start the
+    // moment this grid completes instead of a launch latency later
+    pdl_launch_dependents();
     const int lane = threadIdx.x;
     const int n0 = blockIdx.x * EW;
     const int nty = max(0, min(EW, g.ney - n0));          // the last strip holds the remaining ney % EW rows (maybe none)
@@ -739,6 +743,8 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int k = 0; k < NPD; ++k) pd[R][c][k] = 0.0;
+
+    pdl_wait();   // everything above touched parameters, constant tables and shared memory only
 
     // ---- prologue: carries of line m0*P (x-part from the element on the left, y-part from a y phase over its lines) -------
     {

@@ -4,6 +4,7 @@
 #include "sem_march3.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "sem_dispatch.h"
 
 #ifndef SEM_P
@@ -73,8 +74,27 @@ static int launch_mode3x(const MeshDev& g, const MarchArgs& A, const MarchGeom& 
         for (int k = 0; k < March3Geom<P, MODE>::NSTG; ++k)
             if (tmap_get(f[k], g, March3Geom<P, MODE>::PITCH, P, &TM.m[k])) return -1;
     }
-    sem_march3_kernel<P, MODE, PW, XCH><<<q.grid, 32, smem, st>>>(g, A, X, TM, q.Mx, q.m_lo, q.m_hi);
-    SEM_CUDA(cudaGetLastError());
+    // Programmatic dependent launch (see pdl_wait in the kernel).  SEM_B200_PDL=0: plain launches; default: PDL except while the
+    // stream is being captured into a CUDA graph; 2: also there (programmatic graph edges).
+    static const int pdl = [] { const char* e = std::getenv("SEM_B200_PDL"); return e ? std::atoi(e) : 1; }();
+    bool use_pdl = pdl != 0;
+    if (pdl == 1) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusActive; }
+        use_pdl = cs == cudaStreamCaptureStatusNone;
+    }
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = q.grid;
+    cfg.blockDim = dim3(32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    SEM_CUDA(cudaLaunchKernelEx(&cfg, sem_march3_kernel<P, MODE, PW, XCH>, g, A, X, TM, q.Mx, q.m_lo, q.m_hi));
     return 0;
 }
 

@@ -59,6 +59,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
         : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start as soon
+// as every CTA of the previous kernel in the stream has called pdl_launch_dependents() (or exited); it must call pdl_wait()
+// before it touches anything the previous kernel wrote (returns when that grid has completed and its writes are visible).
+// Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // system-scope release / acquire on a 64-bit flag word (peer memory over NVLink)
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
