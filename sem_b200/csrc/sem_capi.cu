@@ -243,7 +243,7 @@ extern "C" int sem_nccl_unique_id(unsigned char* out128) { return comm_unique_id
 extern "C" int sem_ctx_attach_comm(sem_ctx* c, const unsigned char* id128, int rank, int world) {
     SEM_CHECK_CTX(c);
     if (c->has_comm) { set_error("sem_ctx_attach_comm: communicator already attached"); return -2; }
-    if (comm_init(c->comm, id128, rank, world, c->g.NY)) return -1;
+    if (comm_init(c->comm, id128, rank, world, c->g.NY, c->g.nex)) return -1;
     c->has_comm = 1;
     return 0;
 }
@@ -254,7 +254,7 @@ extern "C" int sem_ctx_attach_loopback(sem_ctx* c) {
     SEM_CHECK_CTX(c);
     if (c->has_comm) { set_error("sem_ctx_attach_loopback: communicator already attached"); return -2; }
     if (!c->g.has_left || !c->g.has_right) { set_error("sem_ctx_attach_loopback: the context must be an inner slab"); return -2; }
-    if (comm_init_loopback(c->comm, c->g.NY)) return -1;
+    if (comm_init_loopback(c->comm, c->g.NY, c->g.nex)) return -1;
     c->has_comm = 1;
     return 0;
 }
@@ -370,14 +370,17 @@ static bool fused_apply_possible(const sem_ctx* c, int mode, int n_fields) {
     int resident = (int)((size_t)c->smem_sm / (ord.smem3(mode) + 1024));
     if (resident > 32) resident = 32;
     if (4 * strips > c->sm_count * resident) return false;
-    const int er = c->g.has_right ? 2 : 0, el = c->g.has_left ? 2 : 0;
-    if (el + er >= c->g.nex) return false;   // no interior
+    // Neighbours must take the same path (the one-launch exchange and the exchange kernels use different mailbox regions and
+    // flags): the choice uses only numbers that are the same on every rank -- the narrowest and the widest slab of the
+    // partition, and two edge chunks of two columns whether this rank has one neighbour or two.
+    if (c->comm.min_nex <= 4) return false;   // some rank would have no interior
     // A large interior (several resident rounds of CTAs) hides the whole exchange of the three-launch path, and the edge CTAs
     // of the one-launch path then only lose time waiting for the neighbour while they hold 2 x strips resident slots:
-    // measured at 2 GPUs on config 5 (512-column slabs) 0.205 ms fused against 0.199 ms split; the 128-column slab of 8 GPUs
-    // takes 66.5 us fused against 71.3 us split (one-GPU loopback).  SEM_B200_FUSED_XCH=2 forces the one-launch path.
+    // measured at 2 GPUs on config 5 (512-column slabs) 0.205 ms fused against 0.199 ms split; 4 GPUs (256 columns) 0.109
+    // against 0.112 ms; the 128-column slab of 8 GPUs takes 66.5 us fused against 71.3 us split (one-GPU loopback).
+    // SEM_B200_FUSED_XCH=2 forces the one-launch path.
     static const bool force = [] { const char* e = std::getenv("SEM_B200_FUSED_XCH"); return e && e[0] == '2'; }();
-    return force || !large_interior(c, c->g.nex - el - er);
+    return force || !large_interior(c, c->comm.max_nex - 4);
 }
 
 static bool large_interior(const sem_ctx* c, int interior_columns) {

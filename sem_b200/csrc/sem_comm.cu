@@ -122,8 +122,9 @@ int comm_fill_xch(const Comm& c, const MeshDev& g, XchArgs& X) {
     return 0;
 }
 
-int comm_init_loopback(Comm& c, int NY) {
+int comm_init_loopback(Comm& c, int NY, int nex) {
     std::memset(&c, 0, sizeof(c));
+    c.min_nex = c.max_nex = nex;
     c.rank = 0;
     c.world = 1;
     c.max_fields = 4;
@@ -190,7 +191,7 @@ static int p2p_init(Comm& c, int NY) {
     return 0;
 }
 
-int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY) {
+int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY, int nex) {
     if (load_nccl()) return -1;
     ncclUniqueId id;
     memcpy(&id, idb, 128);
@@ -204,6 +205,18 @@ int comm_init(Comm& c, const unsigned char idb[128], int rank, int world, int NY
     c.p2p = 0;
     c.box = nullptr;
     c.peer_box[0] = c.peer_box[1] = nullptr;
+    c.loopback = 0;
+    {   // narrowest and widest slab: max over ranks of (-nex, nex)
+        double h[2] = {-(double)nex, (double)nex}, *d = nullptr;
+        SEM_CUDA(cudaMalloc(&d, sizeof(h)));
+        SEM_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+        SEM_NCCL(g_nccl.AllReduce(d, d, 2, ncclDouble, ncclMax, comm, 0));
+        SEM_CUDA(cudaStreamSynchronize(0));
+        SEM_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        c.min_nex = (int)(-h[0] + 0.5);
+        c.max_nex = (int)(h[1] + 0.5);
+    }
     return p2p_init(c, NY);
 }
 

@@ -30,13 +30,15 @@ struct Comm {
     // parity slot with the per-line epochs of the stand-alone exchange kernels.
     size_t fused_off;                // byte offset of that region in a mailbox
     int loopback;                    // self-test on one GPU: this rank is its own left and right neighbour (no NCCL)
+    int min_nex, max_nex;            // narrowest / widest slab of the partition (element columns), agreed at attach time: every
+                                     // choice between exchange paths must come out the same on all ranks
 };
 
 int comm_unique_id(unsigned char out[128]);
-int comm_init(Comm& c, const unsigned char id[128], int rank, int world, int NY);
+int comm_init(Comm& c, const unsigned char id[128], int rank, int world, int NY, int nex);
 // One-GPU self-test of the peer-memory paths: a communicator whose left and right neighbour are this rank itself, so the
 // interface lines of a slab context (has_left / has_right) are exchanged with each other (line 0 <-> last line).
-int comm_init_loopback(Comm& c, int NY);
+int comm_init_loopback(Comm& c, int NY, int nex);
 // arguments of the in-kernel exchange for this rank's slab (peer-memory path only)
 int comm_fill_xch(const Comm& c, const MeshDev& g, XchArgs& X);
 void comm_destroy(Comm& c);

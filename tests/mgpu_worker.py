@@ -176,4 +176,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:                      # the launcher's own error report buries a worker's stderr: say it on stdout
+        import traceback
+        print(f"MGPU_EXC rank {os.environ.get('RANK')}:\n{traceback.format_exc()[-1500:]}", flush=True)
+        raise
