@@ -11,6 +11,7 @@ from sem_b200 import _lib as L
 P, ney = 8, 1024
 nexs = [int(v) for v in sys.argv[1].split(',')] if len(sys.argv) > 1 else [128, 256, 512]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+mxs = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [0]      # chunk lengths (0: the library's choice)
 
 def timeit(fn, n, warm=10):
     for _ in range(warm): fn()
@@ -21,13 +22,15 @@ def timeit(fn, n, warm=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
-for nex in nexs:
+for nex, Mx in [(a, b) for a in nexs for b in mxs]:
     N_ex = 1024
     res = {}
     for kind in ('plain', 'loopback'):
         d = sem_b200.SemDevice(P, N_ex, ney, 1.0 / N_ex, 1.0 / ney, m_begin=nex, m_end=2 * nex)
         if kind == 'loopback':
             L.check(d.lib.sem_ctx_attach_loopback(d.ctx), 'loopback')
+        if Mx:
+            d.set_tiling(0, Mx)
         gen = torch.Generator(device=d.tdev).manual_seed(0)
         def rnd():
             x = d.zeros(); x[:, :d.NY] = torch.randn((d.NX, d.NY), generator=gen, device=d.tdev, dtype=torch.float64); return x
@@ -53,5 +56,5 @@ for nex in nexs:
         torch.cuda.empty_cache()
     nodes = (nex * P + 1) * (ney * P + 1)
     ideal = 32 * nodes / 6531.9e9 * 1e6
-    print(f"CD slab nex={nex:4d}: plain {res['plain']:7.1f} us, loopback ({'one launch' if res['fused'] else 'three launches + exchange kernel'}) "
+    print(f"CD slab nex={nex:4d} Mx={Mx:2d}: plain {res['plain']:7.1f} us, loopback ({'one launch' if res['fused'] else 'three launches + exchange kernel'}) "
           f"{res['loopback']:7.1f} us, HBM-roofline time {ideal:6.1f} us", flush=True)
