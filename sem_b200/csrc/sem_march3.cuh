@@ -76,11 +76,20 @@ struct March3Geom {
     static constexpr int PITCH = POW2 ? NCOLP + ((NCOLP % 4 == 2) ? 0 : 2) : NCOLP + ((18 - NCOLP % 16) % 16);
     static constexpr int TPW = (EW + 1 + 1) & ~1;                        // top-row entries per line
     static constexpr int NSTG = TR::NF + 2 * TR::NV;                     // staged fields: contracted, then U, then V
-    static constexpr int SMEM_DOUBLES = (2 * NSTG + TR::NACC) * P * PITCH + TR::NACC * P * TPW;
-    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 16;
     // One 2-D tensor-map copy per field and step (box = P lines x PITCH columns, which lands with exactly the row pitch of the
-    // tile) when every field's stage starts 128-byte aligned; otherwise P one-line bulk copies per field (16-byte alignment).
-    static constexpr bool TMA2D = (P * PITCH) % 16 == 0;
+    // tile) needs every field's stage to start 128-byte aligned: the stage stride of a field FS is P * PITCH rounded up to
+    // 16 doubles -- unless that padding costs a resident warp per SM (B200: 228 KB of shared memory per SM, 1 KB reserved per
+    // CTA), in which case the order keeps P one-line bulk copies per field (16-byte alignment).
+    static constexpr int FS_NAT = P * PITCH, FS_PAD = (FS_NAT + 15) / 16 * 16;
+    static constexpr int smem_doubles(int fs) { return 2 * NSTG * fs + TR::NACC * P * PITCH + TR::NACC * P * TPW; }
+    static constexpr int resident(int fs) {
+        const int r = 233472 / (smem_doubles(fs) * 8 + 16 + 1024);
+        return r > 32 ? 32 : r;
+    }
+    static constexpr bool TMA2D = resident(FS_PAD) == resident(FS_NAT);
+    static constexpr int FS = TMA2D ? FS_PAD : FS_NAT;
+    static constexpr int SMEM_DOUBLES = smem_doubles(FS);
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 16;
     static_assert(EW * P / NC <= 32 && (P / NL) * EW <= 32, "a strip must fit one warp in both phases");
 };
 
@@ -116,7 +125,7 @@ struct March3 {
     static constexpr bool MID = (P % 2 == 0);                 // even order: row / column P/2 has no partner
     static __host__ __device__ constexpr bool has_partner(int I) { return !(MID && I == HE - 1); }
     static constexpr int NF = MM::NF, NV = MM::NV, NACC = MM::NACC, NOUT = MM::NOUT;
-    static constexpr int NC = GE::NC, NL = GE::NL, EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, NSTG = GE::NSTG;
+    static constexpr int NC = GE::NC, NL = GE::NL, EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, NSTG = GE::NSTG, FS = GE::FS;
     static constexpr int G = P / NL;   // lanes per element in the y phase
     static constexpr bool HAS_BC = (MODE == MODE_CD || MODE == MODE_NS);
     static constexpr bool NODE_FAST = (MODE == MODE_NS) && PW;   // the NS JVP multiplies the node values by pointwise diagonals
@@ -241,7 +250,7 @@ struct March3 {
         for (int l = 0; l < NL; ++l)
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const double* row = sB + (f * P + sp + l * G) * PITCH + col0;
+                const double* row = sB + f * FS + (sp + l * G) * PITCH + col0;
                 double a[n];
                 if constexpr (V2) {
 #pragma unroll
@@ -257,7 +266,7 @@ struct March3 {
                 }
                 fold(a, e[l][f], o[l][f]);
             }
-        const double* sV = sB + ((NF + 1) * P + sp) * PITCH + col0;   // V line of slot sp (NV modes)
+        const double* sV = sB + (NF + 1) * FS + sp * PITCH + col0;   // V line of slot sp (NV modes)
         if constexpr (FULLROWS) {
             double Y[NL][NACC][n];
             static_for<0, HE>([&](auto Jc) {
@@ -407,7 +416,7 @@ struct March3 {
                 if (side < 0 && !pin) continue;
                 const int off = ix * g.LD + iy;
                 double nv[NF];
-                for (int f = 0; f < NF; ++f) nv[f] = (R == 0) ? aprev[c * NF + f] : sB[(f * P + R - 1) * PITCH + c0 + c];
+                for (int f = 0; f < NF; ++f) nv[f] = (R == 0) ? aprev[c * NF + f] : sB[f * FS + (R - 1) * PITCH + c0 + c];
                 if (side >= 0) {
                     A.y0[off] = nv[0] - (A.bc.residual ? A.bc.val0[side] : 0.0);
                     if constexpr (MODE == MODE_NS) A.y1[off] = nv[1] - (A.bc.residual ? A.bc.val1[side] : 0.0);
@@ -449,7 +458,7 @@ struct March3 {
             }
 #pragma unroll
             for (int k = 1; k <= P; ++k) {
-                const VecN<NC> v = ld_vec<NC>(sB + (f * P + (k - 1)) * PITCH + c0);
+                const VecN<NC> v = ld_vec<NC>(sB + f * FS + (k - 1) * PITCH + c0);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) a[c][k] = v.v[c];
             }
@@ -471,7 +480,7 @@ struct March3 {
         };
         auto load_U = [&](int R, double (&Uc)[NC]) {
             if constexpr (NV) {
-                const VecN<NC> v = ld_vec<NC>(sB + (NF * P + (R - 1)) * PITCH + c0);
+                const VecN<NC> v = ld_vec<NC>(sB + NF * FS + (R - 1) * PITCH + c0);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) Uc[c] = v.v[c];
             } else {
@@ -485,7 +494,7 @@ struct March3 {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) node[c][f] = 0.0;
                 if constexpr (NODE_FAST) {
-                    const VecN<NC> v = ld_vec<NC>(sB + (f * P + (R - 1)) * PITCH + c0);
+                    const VecN<NC> v = ld_vec<NC>(sB + f * FS + (R - 1) * PITCH + c0);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) node[c][f] = v.v[c];
                 }
@@ -613,10 +622,10 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     using M3 = March3<P, MODE, PW>;
     using GE = March3Geom<P, MODE>;
     constexpr int NF = M3::NF, NACC = M3::NACC, NOUT = M3::NOUT, NSTG = M3::NSTG, NC = M3::NC, NL = M3::NL, G = M3::G;
-    constexpr int EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW;
-    constexpr int STAGE = NSTG * P * PITCH;               // doubles per stage
+    constexpr int EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, FS = GE::FS;
+    constexpr int STAGE = NSTG * FS;                      // doubles per stage (FS: stage stride of a field, >= P * PITCH)
     extern __shared__ __align__(128) double smem3[];
-    double* sS = smem3;                                   // [2][NSTG][P][PITCH] staged node lines (TMA destination)
+    double* sS = smem3;                                   // [2][NSTG] field stages of FS doubles: [P][PITCH] staged node lines (TMA destination)
     double* sA = sS + 2 * STAGE;                          // [NACC][P][PITCH]    y-part rows 0..P-1 of every element line
     double* sT = sA + NACC * P * PITCH;                   // [NACC][P][TPW]      y-part row P (node shared with the element above)
     uint64_t* bar = reinterpret_cast<uint64_t*>(sT + NACC * P * TPW);   // [2]
@@ -708,13 +717,13 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
                 mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * P * PITCH * 8));
 #pragma unroll
                 for (int f = 0; f < NSTG; ++f)
-                    tma_load_2d(sS + buf * STAGE + f * P * PITCH, &TM.m[f], ybase, line_first - slot_first, &bar[buf]);
+                    tma_load_2d(sS + buf * STAGE + f * FS, &TM.m[f], ybase, line_first - slot_first, &bar[buf]);
             } else {
                 mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
 #pragma unroll
                 for (int f = 0; f < NSTG; ++f) {
                     const double* src = field(f) + (size_t)line_first * g.LD + ybase;
-                    double* dst = sS + buf * STAGE + (f * P + slot_first) * PITCH;
+                    double* dst = sS + buf * STAGE + f * FS + slot_first * PITCH;
                     for (int k = 0; k < nlines; ++k) bulk_g2s(dst + k * PITCH, src + (size_t)k * g.LD, line_bytes, &bar[buf]);
                 }
             }
@@ -773,12 +782,12 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
             } else {
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    const VecN<NC> v = ld_vec<NC>(sB + (f * P + (P - 1)) * PITCH + c0);
+                    const VecN<NC> v = ld_vec<NC>(sB + f * FS + (P - 1) * PITCH + c0);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) a0[c][f] = v.v[c];
                 }
                 if constexpr (M3::NV) {
-                    const VecN<NC> v = ld_vec<NC>(sB + (NF * P + (P - 1)) * PITCH + c0);
+                    const VecN<NC> v = ld_vec<NC>(sB + NF * FS + (P - 1) * PITCH + c0);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) U0[c] = v.v[c];
                 }

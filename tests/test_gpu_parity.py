@@ -1,7 +1,8 @@
 """GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes numpy -> Python drop-in class -> ctypes ->
 C ABI -> sm_100a kernels.  Checked against (1) the committed outputs of the unmodified reference (tests/golden) and
 (2) the CPU oracle on seeded inputs.  Tolerances: operator applies <= 1e-12 relative L2 (north_star), converged
-fields <= 1e-8 relative L2 (pressure on the C3 mesh: 2e-7, the reference's own convergence floor there)."""
+fields <= 1e-8 relative L2 (pressure on the C3 mesh: 2e-7 against the reference's stored field, which stops at the reference's own
+convergence floor, and <= 1e-8 against the oracle converged to 5e-15)."""
 import os
 
 import numpy as np
@@ -184,10 +185,26 @@ def test_ns_solution_matches_reference(sem, golden, tag, kw, solve):
     u0, v0, p0 = (np.zeros(ns.N) for _ in range(3))
     u, v, p = ns._get_solution(k("T_in"), u0=u0, v0=v0, p0=p0)
     assert u is u0 and v is v0 and p is p0                       # in-place contract of NS:248-267
-    ptol = 2e-7 if tag == "c3" else FIELD_TOL                    # see tests/test_oracle.py
+    # The stored C3 fields stop at the reference's own floor: its Schur LGMRES ends at |res| <= 1e-13 sqrt(N) and the 8x8 mesh's
+    # smallest singular values (~1e-5) turn that into 6.4e-8 in p -- the oracle converged to 5e-15 by direct solves differs from
+    # the stored p by exactly that (tests/test_oracle.py).  Against the stored fields the pressure gate is therefore 2e-7; the
+    # 1e-8 gate of the north star is applied against the tightly converged oracle below.
+    ptol = 2e-7 if tag == "c3" else FIELD_TOL
     assert relerr(u, k("u_sol")) < FIELD_TOL and relerr(v, k("v_sol")) < FIELD_TOL
     assert relerr(p, k("p_sol")) < ptol
     assert ns._k == int(k("newton_its"))
+    if tag == "c3":
+        from oracle import sem_oracle as so                      # checker
+        o = so.NSOracle(mtol=1e-15, mtol_newton=1e-15, **kw)
+        uo, vo, po = o._get_solution(k("T_in"))
+        ro = np.hstack(o._get_residuals(uo, vo, po, k("T_in")))
+        assert np.linalg.norm(ro) < 1e-13                        # measured 5.5e-15
+        assert relerr(po, k("p_sol")) < ptol                     # the same 6.4e-8 as the GPU against the stored field
+        for precond in ("fdm", "full"):                          # measured against the oracle: p 5.8e-10 / 5.9e-12
+            nt = sem.NavierStokesSolver(mtol=1e-14, mtol_newton=1e-14, iprint=[], precond=precond, **kw)
+            ut, vt, pt = nt._get_solution(k("T_in"))
+            assert relerr(ut, uo) < FIELD_TOL and relerr(vt, vo) < FIELD_TOL and relerr(pt, po) < FIELD_TOL, precond
+            assert nt._k == o._k
     # linear update about the converged state (reference solved it to mtol = 1e-11 only)
     ns._get_residuals(k("u_sol"), k("v_sol"), k("p_sol"), k("T_in"))
     ns._calc_jacobians(k("u_sol"), k("v_sol"))
