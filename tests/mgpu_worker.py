@@ -78,7 +78,9 @@ def main():
     # ---- the partitioned NS preconditioner (distributed fast-diagonalisation plans, ring Chebyshev with interface exchange,
     #      all-reduced projector coefficients and member dots): every stage against the CPU mirror, then a Newton solve with it
     from oracle.ns_precond import NSPrecondMirror
-    for (Pq, nxq, nyq, Re) in ((4, 2 * world, 6, 80.0), (3, nex_ns, 4, 40.0)):
+    # 6 element columns per rank: wide enough for the one-launch (in-kernel exchange) applies inside the stages; the second
+    # mesh has slabs of 1-2 columns (exchange kernels)
+    for (Pq, nxq, nyq, Re) in ((4, 6 * world, 6, 80.0), (3, nex_ns, 4, 40.0)):
         qkw = dict(L_x=1.2, L_y=0.9, Re=Re, Gr=0.0, P=Pq, N_ex=nxq, N_ey=nyq, u_N=1.0, v_W=0.2)
         part = Partition(nxq, nyq, Pq, rank, world)
         sl = part.local_slice
