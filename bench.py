@@ -257,6 +257,40 @@ def run_ours(args):
         t = torch.tensor([e2e_pageable_s], device=d.tdev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_pageable_s = float(t.item())
+    # The host link under the same load, without any of our code: every rank copies its pinned slab up and another pinned
+    # slab down concurrently (full duplex), all ranks at once.  e2e can at best move 2 x n_local x 8 bytes in that time.
+    link = None
+    try:
+        up_dev = torch.empty(n_local, dtype=torch.float64, device=d.tdev)
+        dn_dev = torch.randn(n_local, dtype=torch.float64, device=d.tdev)
+        dn_host = torch.empty(n_local, dtype=torch.float64).pin_memory()
+        up_host = torch.from_numpy(host_in)
+        s_up, s_dn = torch.cuda.Stream(d.tdev), torch.cuda.Stream(d.tdev)
+
+        def duplex():
+            with torch.cuda.stream(s_up):
+                up_dev.copy_(up_host, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                dn_host.copy_(dn_dev, non_blocking=True)
+
+        duplex()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            duplex()
+        sync_all()
+        link_s = (time.perf_counter() - t0) / 3
+        if world > 1:
+            t = torch.tensor([link_s], device=d.tdev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            link_s = float(t.item())
+        link = {"ms_per_duplex_copy": link_s * 1e3, "gb_s_each_way_per_rank": n_local * 8 / link_s / 1e9,
+                "gb_s_each_way_aggregate": world * n_local * 8 / link_s / 1e9,
+                "e2e_ceiling_gdof_s": n_global / link_s / 1e9,
+                "note": "torch pinned copies of one slab up and one down on two streams, all ranks at once; no sem_b200 code"}
+        del up_dev, dn_dev, dn_host, up_host
+    except Exception as exc:                          # a probe must not lose the headline line
+        link = {"error": str(exc)[:200]}
     del res_host, pageable_in, host_in
 
     parity = partition_parity(sem_b200, rank, world, local) if world > 1 else None
@@ -320,6 +354,7 @@ def run_ours(args):
         "e2e": {"value": n_global / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n_local * 8),
                 "d2h_bytes_per_step": int(n_local * 8), "ms_per_step": e2e_s * 1e3,
                 "api": "ConvectionDiffusionSolver._get_dresiduals(numpy pinned) -> numpy",
+                "host_link": link,
                 "pageable_input": {"value": n_global / e2e_pageable_s / 1e9, "ms_per_step": e2e_pageable_s * 1e3,
                                    "note": "same call with an ordinary numpy array (what OpenMDAO passes); result still lands "
                                            "in a recycled page-locked block"}},

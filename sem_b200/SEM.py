@@ -76,19 +76,58 @@ def _device_for(P, N_ex, N_ey, dx=1.0, dy=1.0, _cache={}):
 
 
 def assemble(A_e: np.ndarray):
-    """Gather-scatter of a 4-index element array A[m,n,i,j] into a global vector  (SEM.py:113-131).
+    """Gather-scatter of an element array into global numbering  (SEM.py:113-146).
 
-    Runs the colour-ordered, atomic-free device kernel (bitwise reproducible).  6- and 8-index arrays are what the
-    matrix-free path removes; use ``global_*_matrix`` (matrix-free operators) instead.
+    4-index ``A[m,n,i,j]`` -> global vector: the colour-ordered, atomic-free device kernel (bitwise reproducible).
+    6-index ``A[m,n,i,j,k,l]`` -> SciPy CSR matrix and 8-index ``A[m,n,i,j,r,s,k,l]`` -> a sparse 3-tensor (:class:`COO3`, the
+    stand-in for ``sparse.COO``; contract it with :func:`tensordot`): host-side convenience paths for callers outside the two
+    solvers -- the solvers themselves never form these arrays (``global_*_matrix`` return matrix-free operators).
     """
     A_e = np.asarray(A_e, dtype=np.float64)
-    if A_e.ndim != 4:
-        raise NotImplementedError("sem_b200 assembles 4-index element arrays; element matrices are applied "
-                                  "matrix-free (see global_stiffness_matrix / global_gradient_matrices)")
+    if A_e.ndim not in (4, 6, 8):
+        raise ValueError("assemble expects a 4-, 6- or 8-index element array")
     N_ex, N_ey, P = A_e.shape[0], A_e.shape[1], A_e.shape[2] - 1
-    dev = _device_for(P, N_ex, N_ey)
-    elem = torch.from_numpy(np.ascontiguousarray(A_e)).to(dev.tdev)
-    return dev.to_host(dev.gather_scatter(elem))
+    if A_e.ndim == 4:
+        dev = _device_for(P, N_ex, N_ey)
+        elem = torch.from_numpy(np.ascontiguousarray(A_e)).to(dev.tdev)
+        return dev.to_host(dev.gather_scatter(elem))
+    import scipy.sparse as sp_sparse
+    N = (P * N_ex + 1) * (P * N_ey + 1)
+    nz = np.nonzero(A_e)
+    m, n = nz[0], nz[1]
+    idx = [global_index(P, N_ex, N_ey, m, n, nz[2 + 2 * t], nz[3 + 2 * t]) for t in range(A_e.ndim // 2 - 1)]
+    data = A_e[nz]
+    if A_e.ndim == 6:                                  # duplicates (shared nodes) are summed by the conversion
+        return sp_sparse.coo_matrix((data, (idx[0], idx[1])), shape=(N, N)).tocsr()
+    return COO3(np.vstack(idx), data, (N, N, N))
+
+
+class COO3:
+    """Minimal sparse 3-tensor in coordinate format (duplicates are summed on contraction): what ``SEM.assemble`` returns for
+    8-index element arrays in place of ``sparse.COO`` (SEM.py:139-145; the ``sparse`` package is not a dependency here)."""
+
+    def __init__(self, coords, data, shape):
+        self.coords, self.data, self.shape = np.asarray(coords), np.asarray(data, dtype=np.float64), tuple(shape)
+
+    def tensordot(self, v, axis):
+        """Contract index ``axis`` (0, 1 or 2) with the vector ``v`` -> SciPy CSR matrix over the remaining two indices."""
+        import scipy.sparse as sp_sparse
+        v = np.asarray(v, dtype=np.float64)
+        keep = [a for a in range(3) if a != axis]
+        return sp_sparse.coo_matrix((self.data * v[self.coords[axis]], (self.coords[keep[0]], self.coords[keep[1]])),
+                                    shape=(self.shape[keep[0]], self.shape[keep[1]])).tocsr()
+
+    def __matmul__(self, v):          # numpy semantics of C @ v: the last index
+        return self.tensordot(v, 2)
+
+    def __rmatmul__(self, v):         # numpy semantics of v @ C: the second-to-last index
+        return self.tensordot(v, 1)
+
+
+def tensordot(C, v, axes, return_type=None):
+    """``sparse.tensordot(C, v, (axis, 0), return_type=sparse.COO)`` of the reference (CD:82-83,101-102; NS:103-104,130-136) for
+    the 3-tensors of this package (:class:`COO3`, :class:`_Convection3`): contracts index ``axes[0]`` of ``C`` with ``v``."""
+    return C.tensordot(v, int(axes[0]))
 
 
 def scatter(u: np.ndarray, P: int, N_ex: int, N_ey: int):
@@ -143,10 +182,48 @@ def global_gradient_matrices(P, N_ex, N_ey, dx, dy):
     return _MatrixFree(dev, 'Gx'), _MatrixFree(dev, 'Gy')
 
 
+class _RowScaled:
+    """``diag(u) G``: what ``u @ C`` is for a convection tensor; ``@ x`` launches the matrix-free gradient."""
+
+    def __init__(self, u, G):
+        self._u, self._G, self.shape = np.asarray(u, dtype=np.float64), G, G.shape
+
+    def __matmul__(self, x):
+        return self._u * (self._G @ x)
+
+
+class _Convection3:
+    """Stand-in for the N x N x N convection tensors of SEM.py:226-245.  With the Kronecker deltas of GLL.py:84-102 the tensor
+    is diagonal in its first two indices, ``C[a, b, c] = delta_ab G[a, c]``, so it is never formed:
+    ``tensordot(C, u, (1, 0)) == u @ C == diag(u) G`` (matrix-free operator) and ``tensordot(C, T, (2, 0)) == C @ T ==
+    diag(G T)`` (SciPy sparse diagonal matrix)."""
+
+    def __init__(self, G):
+        self._G = G
+        self.shape = (G.shape[0],) * 3
+
+    def tensordot(self, v, axis):
+        import scipy.sparse as sp_sparse
+        if axis == 1:
+            return _RowScaled(v, self._G)
+        if axis == 2:
+            return sp_sparse.diags(self._G @ v, format='csr')
+        raise NotImplementedError("a convection tensor is contracted over its velocity (1) or its field (2) index")
+
+    def __matmul__(self, T):
+        return self.tensordot(T, 2)
+
+    def __rmatmul__(self, u):
+        return self.tensordot(u, 1)
+
+    __array_ufunc__ = None            # let ``ndarray @ C`` reach __rmatmul__
+
+
 def global_convection_matrices(P, N_ex, N_ey, dx, dy):
-    """The N x N x N tensors of SEM.py:226-245 are never built: ``u @ C_x == diag(u) G_x`` and
-    ``C_x @ T == diag(G_x T)``; the solvers use those identities inside the fused kernels."""
-    raise NotImplementedError("convection tensors are applied matrix-free: u@C_x = diag(u) G_x, C_x@T = diag(G_x T)")
+    """C_x, C_y of SEM.py:226-245 as matrix-free stand-ins (:class:`_Convection3`); contract them with :func:`tensordot`, ``@``
+    or ``u @ C``.  The solvers use the same identities inside the fused kernels."""
+    Gx, Gy = global_gradient_matrices(P, N_ex, N_ey, dx, dy)
+    return _Convection3(Gx), _Convection3(Gy)
 
 
 def interp_matrix_1d(P: int, N_e: int, h: float, pts: np.ndarray) -> np.ndarray:

@@ -565,3 +565,21 @@ def test_partitioned_apply_loopback_exchange(sem, P, nex, ney, expect_fused, fus
         return
     from tests.loopback_check import check
     check(sem, P, nex, ney, expect_fused=expect_fused)
+
+
+def test_convection_tensor_stand_ins(sem):
+    """SEM.global_convection_matrices (SEM.py:226-245) as matrix-free stand-ins: u @ C_x = diag(u) G_x and C_x @ T = diag(G_x T),
+    the two contractions the reference's solvers make (CD:82-83,101-102), against the oracle's assembled gradient matrices."""
+    from oracle import sem_oracle as so                          # checker
+    P, nx, ny, dx, dy = 4, 5, 3, 0.3, 0.4
+    Cx, Cy = sem.SEM.global_convection_matrices(P, nx, ny, dx, dy)
+    _, _, Gx, Gy = so.global_operators(P, nx, ny, dx, dy)
+    rng = np.random.default_rng(2)
+    N = Gx.shape[0]
+    u, T = rng.standard_normal(N), rng.standard_normal(N)
+    for C, G in ((Cx, Gx), (Cy, Gy)):
+        assert C.shape == (N, N, N)
+        assert relerr(sem.SEM.tensordot(C, u, (1, 0)) @ T, u * (G @ T)) < APPLY_TOL
+        assert relerr((u @ C) @ T, u * (G @ T)) < APPLY_TOL
+        assert relerr(sem.SEM.tensordot(C, T, (2, 0)).diagonal(), G @ T) < APPLY_TOL
+        assert relerr((C @ T) @ u, (G @ T) * u) < APPLY_TOL

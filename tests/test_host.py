@@ -153,3 +153,45 @@ def test_header_is_plain_c():
     res = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_assemble_matrix_and_tensor_element_arrays():
+    """SEM.assemble for 6- and 8-index element arrays (SEM.py:132-145) -- host paths, no GPU: against a brute-force dense
+    accumulation over the global index map, and the 6-index stiffness against the oracle's assembled matrix."""
+    from sem_b200 import SEM, GLL
+    from oracle import sem_oracle as so
+    P, nx, ny, dx, dy = 3, 3, 2, 0.7, 1.3
+    n, N = P + 1, (P * nx + 1) * (P * ny + 1)
+    rng = np.random.default_rng(5)
+    A6 = rng.standard_normal((nx, ny, n, n, n, n)) * (rng.random((nx, ny, n, n, n, n)) < 0.3)
+    dense = np.zeros((N, N))
+    A8 = rng.standard_normal((nx, ny, n, n, n, n, n, n)) * (rng.random((nx, ny, n, n, n, n, n, n)) < 0.05)
+    dense3 = np.zeros((N, N, N))
+    gi = lambda m, e, i, j: int(SEM.global_index(P, nx, ny, m, e, i, j))
+    for m in range(nx):
+        for e in range(ny):
+            for i in range(n):
+                for j in range(n):
+                    a = gi(m, e, i, j)
+                    for k in range(n):
+                        for l in range(n):
+                            b = gi(m, e, k, l)
+                            dense[a, b] += A6[m, e, i, j, k, l]
+                            for r in range(n):
+                                for q in range(n):
+                                    dense3[a, b, gi(m, e, r, q)] += A8[m, e, i, j, k, l, r, q]
+    assert np.abs(SEM.assemble(A6).toarray() - dense).max() < 1e-14
+    C = SEM.assemble(A8)
+    u = rng.standard_normal(N)
+    assert np.abs(SEM.tensordot(C, u, (1, 0)).toarray() - np.einsum('abc,b->ac', dense3, u)).max() < 1e-12
+    assert np.abs(SEM.tensordot(C, u, (2, 0)).toarray() - np.einsum('abc,c->ab', dense3, u)).max() < 1e-12
+    assert np.abs((C @ u).toarray() - np.einsum('abc,c->ab', dense3, u)).max() < 1e-12
+    # the element stiffness array of SEM.py:186-203, assembled, is the oracle's K
+    w, Ks = GLL.standard_nodes(P)[1], GLL.standard_stiffness_matrix(P)
+    Ke = (2.0 / dx) * (dy / 2.0) * np.einsum('ik,j,jl->ijkl', Ks, w, np.eye(n)) \
+        + (dx / 2.0) * (2.0 / dy) * np.einsum('i,ik,jl->ijkl', w, np.eye(n), Ks)
+    K = SEM.assemble(np.broadcast_to(Ke, (nx, ny) + Ke.shape).copy())
+    Ko = so.global_operators(P, nx, ny, dx, dy)[1]
+    assert abs(K - Ko).max() < 1e-12
+    with pytest.raises(ValueError):
+        SEM.assemble(np.zeros((2, 2, 3)))
