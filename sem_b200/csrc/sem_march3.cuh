@@ -80,16 +80,29 @@ struct March3Geom {
     // tile) needs every field's stage to start 128-byte aligned: the stage stride of a field FS is P * PITCH rounded up to
     // 16 doubles -- unless that padding costs a resident warp per SM (B200: 228 KB of shared memory per SM, 1 KB reserved per
     // CTA), in which case the order keeps P one-line bulk copies per field (16-byte alignment).
+    // SPLIT (NS): the contracted fields are double-buffered, the two advecting components have ONE stage each with their own
+    // mbarriers -- V is consumed by the y phase and refilled right after it, U by the x phase and refilled after that, so each
+    // refill still has the other phase of the step to arrive.  Two field stages less per warp: 30.7 instead of 36.1 KB at
+    // P = 8, 7 instead of 6 resident warps per SM.  Measured at 67 M nodes (NS Jacobian apply, ms before -> after): P = 4 1.138 ->
+    // 1.036 (95 % of the roofline), P = 8 1.243 -> 1.221 (81 %), P = 12 2.99 -> 2.76, P = 16 3.98 -> 2.95; P = 10 loses its 2-D
+    // tensor maps to the padding rule below and part of its uniform table operands (1.90 -> 2.09) and stays double-buffered.
+    // SEM_NO_SPLIT_UV builds the fully double-buffered NS kernel of every order for A/B runs.
+#ifdef SEM_NO_SPLIT_UV
+    static constexpr bool SPLIT = false;
+#else
+    static constexpr bool SPLIT = (MODE == MODE_NS) && P != 10;
+#endif
+    static constexpr int NSTAGES = SPLIT ? 2 * TR::NF + 2 * TR::NV : 2 * NSTG;     // field stages per warp
     static constexpr int FS_NAT = P * PITCH, FS_PAD = (FS_NAT + 15) / 16 * 16;
-    static constexpr int smem_doubles(int fs) { return 2 * NSTG * fs + TR::NACC * P * PITCH + TR::NACC * P * TPW; }
+    static constexpr int smem_doubles(int fs) { return NSTAGES * fs + TR::NACC * P * PITCH + TR::NACC * P * TPW; }
     static constexpr int resident(int fs) {
-        const int r = 233472 / (smem_doubles(fs) * 8 + 16 + 1024);
+        const int r = 233472 / (smem_doubles(fs) * 8 + 32 + 1024);
         return r > 32 ? 32 : r;
     }
     static constexpr bool TMA2D = resident(FS_PAD) == resident(FS_NAT);
     static constexpr int FS = TMA2D ? FS_PAD : FS_NAT;
     static constexpr int SMEM_DOUBLES = smem_doubles(FS);
-    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 16;
+    static constexpr size_t SMEM_BYTES = (size_t)SMEM_DOUBLES * 8 + 32;   // + 4 mbarriers
     static_assert(EW * P / NC <= 32 && (P / NL) * EW <= 32, "a strip must fit one warp in both phases");
 };
 
@@ -126,6 +139,7 @@ struct March3 {
     static __host__ __device__ constexpr bool has_partner(int I) { return !(MID && I == HE - 1); }
     static constexpr int NF = MM::NF, NV = MM::NV, NACC = MM::NACC, NOUT = MM::NOUT;
     static constexpr int NC = GE::NC, NL = GE::NL, EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, NSTG = GE::NSTG, FS = GE::FS;
+    static constexpr bool SPLIT = GE::SPLIT;
     static constexpr int G = P / NL;   // lanes per element in the y phase
     static constexpr bool HAS_BC = (MODE == MODE_CD || MODE == MODE_NS);
     static constexpr bool NODE_FAST = (MODE == MODE_NS) && PW;   // the NS JVP multiplies the node values by pointwise diagonals
@@ -236,8 +250,8 @@ struct March3 {
     // Every lane computes (convergent code keeps the table fetches on the uniform datapath); `active` guards the stores.
     template <bool FULLROWS>
     static __device__ __forceinline__ void yitem(bool active, int sp, int col0, int topslot, const double (&wx)[NL], double cc,
-                                                 double ky, const double* __restrict__ sB, double* __restrict__ sA,
-                                                 double* __restrict__ sT, int z) {
+                                                 double ky, const double* __restrict__ sB, const double* __restrict__ sVb,
+                                                 double* __restrict__ sA, double* __restrict__ sT, int z) {
         double cky[NL], ccw[NL];
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
@@ -266,7 +280,8 @@ struct March3 {
                 }
                 fold(a, e[l][f], o[l][f]);
             }
-        const double* sV = sB + (NF + 1) * FS + sp * PITCH + col0;   // V line of slot sp (NV modes)
+        // V line of slot sp (NV modes): in the stage of the buffer, or (SPLIT) in the single V stage sVb
+        const double* sV = (SPLIT ? sVb : sB + (NF + 1) * FS) + sp * PITCH + col0;
         if constexpr (FULLROWS) {
             double Y[NL][NACC][n];
             static_for<0, HE>([&](auto Jc) {
@@ -331,15 +346,15 @@ struct March3 {
     // top row of the element below the strip (its node j = 0 is tile column halo - P) -> sT[line][0].  wx: x-weights of the
     // slots (lane % G) + l*G -- the same for both passes because q < G implies q % G == q.
     static __device__ __forceinline__ void yphase(int nty, int halo, const double (&wx)[NL], double cc, double ky,
-                                                  const double* __restrict__ sB, double* __restrict__ sA,
-                                                  double* __restrict__ sT, int z) {
+                                                  const double* __restrict__ sB, const double* __restrict__ sVb,
+                                                  double* __restrict__ sA, double* __restrict__ sT, int z) {
         const int q = threadIdx.x;
         const int sp = q % G;
         const int nn = q / G;
         // Divergent on purpose: running both passes with all lanes and guarded stores measured slower (CD 0.48 ms against
         // 0.39 ms at config 5: the convergent code spills uniform registers, R2UR.FILL).
-        if (q < G * nty) yitem<true>(true, sp, halo + nn * P, nn + 1, wx, cc, ky, sB, sA, sT, z);
-        if (halo > 0 && q < G) yitem<false>(true, sp, halo - P, 0, wx, cc, ky, sB, sA, sT, z);
+        if (q < G * nty) yitem<true>(true, sp, halo + nn * P, nn + 1, wx, cc, ky, sB, sVb, sA, sT, z);
+        if (halo > 0 && q < G) yitem<false>(true, sp, halo - P, 0, wx, cc, ky, sB, sVb, sA, sT, z);
     }
 
     // store the NOUT outputs of the lane's NC nodes of line ix
@@ -436,7 +451,8 @@ struct March3 {
     template <bool FULL>
     static __device__ __forceinline__ void xphase(const MeshDev& g, const MarchArgs& A, int m, int iy0, int c0, int topi,
                                                   const bool (&own)[NC], bool colflag, const double* __restrict__ sB,
-                                                  const double* __restrict__ sA, const double* __restrict__ sT,
+                                                  const double* __restrict__ sUb, const double* __restrict__ sA,
+                                                  const double* __restrict__ sT,
                                                   const double (&wyA)[NC], double cc, double (&a0)[NC][NF],
                                                   double (&U0)[NC], double (&xc)[NC][NOUT], double (&yc)[NC][NACC],
                                                   const double (&pd)[P][NC][NPD], int z) {
@@ -480,7 +496,7 @@ struct March3 {
         };
         auto load_U = [&](int R, double (&Uc)[NC]) {
             if constexpr (NV) {
-                const VecN<NC> v = ld_vec<NC>(sB + NF * FS + (R - 1) * PITCH + c0);
+                const VecN<NC> v = ld_vec<NC>((SPLIT ? sUb : sB + NF * FS) + (R - 1) * PITCH + c0);
 #pragma unroll
                 for (int c = 0; c < NC; ++c) Uc[c] = v.v[c];
             } else {
@@ -623,12 +639,16 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     using GE = March3Geom<P, MODE>;
     constexpr int NF = M3::NF, NACC = M3::NACC, NOUT = M3::NOUT, NSTG = M3::NSTG, NC = M3::NC, NL = M3::NL, G = M3::G;
     constexpr int EW = GE::EW, PITCH = GE::PITCH, TPW = GE::TPW, FS = GE::FS;
-    constexpr int STAGE = NSTG * FS;                      // doubles per stage (FS: stage stride of a field, >= P * PITCH)
+    constexpr bool SPLIT = GE::SPLIT;                     // single U and V stages with their own barriers (NS)
+    constexpr int NBUF = SPLIT ? NF : NSTG;               // fields in a double-buffered stage
+    constexpr int STAGE = NBUF * FS;                      // doubles per stage (FS: stage stride of a field, >= P * PITCH)
     extern __shared__ __align__(128) double smem3[];
-    double* sS = smem3;                                   // [2][NSTG] field stages of FS doubles: [P][PITCH] staged node lines (TMA destination)
-    double* sA = sS + 2 * STAGE;                          // [NACC][P][PITCH]    y-part rows 0..P-1 of every element line
+    double* sS = smem3;                                   // [2][NBUF] field stages of FS doubles: [P][PITCH] staged node lines (TMA destination)
+    double* sU1 = sS + 2 * STAGE;                         // SPLIT: the U stage, then the V stage
+    double* sV1 = sU1 + FS;
+    double* sA = sS + GE::NSTAGES * FS;                   // [NACC][P][PITCH]    y-part rows 0..P-1 of every element line
     double* sT = sA + NACC * P * PITCH;                   // [NACC][P][TPW]      y-part row P (node shared with the element above)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sT + NACC * P * TPW);   // [2]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sT + NACC * P * TPW);   // [4]: stage 0, stage 1, U, V
 
     // back-to-back applies: the next launch may place its CTAs as soon as all of ours have started, i.e. into the slots our
     // tail frees; its set-up (barriers, accumulator clear, weights) then overlaps our tail and its first loads start the
@@ -700,6 +720,10 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     if (lane == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        if constexpr (SPLIT) {
+            mbar_init(&bar[2], 1);
+            mbar_init(&bar[3], 1);
+        }
         mbar_fence_init();
     }
     // the accumulator column of the topmost mesh node and the halo entry of sT are never written by the y phase
@@ -711,25 +735,37 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
     // and the compiler serialises the lanes with an ELECT loop, ~10 instructions per copy.)
     // With tensor maps (GE::TMA2D) the same call is ONE copy per field: the box of P lines x PITCH columns whose slot
     // `slot_first` is line `line_first`; lines before line 0 (the one-line call of the prologue) arrive as zeros.
-    auto issue = [&](int buf, int line_first, int nlines, int slot_first) {
+    // copies of the fields [f_lo, f_hi) into the stage that starts at `dst` (field f at dst + (f - f_lo) * FS), on barrier bp
+    auto issue_fields = [&](double* dst, uint64_t* bp, int f_lo, int f_hi, int line_first, int nlines, int slot_first) {
         if (elect_one()) {
             if constexpr (GE::TMA2D) {
-                mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * P * PITCH * 8));
+                mbar_expect_tx(bp, (uint32_t)((f_hi - f_lo) * P * PITCH * 8));
 #pragma unroll
                 for (int f = 0; f < NSTG; ++f)
-                    tma_load_2d(sS + buf * STAGE + f * FS, &TM.m[f], ybase, line_first - slot_first, &bar[buf]);
+                    if (f >= f_lo && f < f_hi) tma_load_2d(dst + (f - f_lo) * FS, &TM.m[f], ybase, line_first - slot_first, bp);
             } else {
-                mbar_expect_tx(&bar[buf], (uint32_t)(NSTG * nlines) * line_bytes);
+                mbar_expect_tx(bp, (uint32_t)((f_hi - f_lo) * nlines) * line_bytes);
 #pragma unroll
-                for (int f = 0; f < NSTG; ++f) {
-                    const double* src = field(f) + (size_t)line_first * g.LD + ybase;
-                    double* dst = sS + buf * STAGE + f * FS + slot_first * PITCH;
-                    for (int k = 0; k < nlines; ++k) bulk_g2s(dst + k * PITCH, src + (size_t)k * g.LD, line_bytes, &bar[buf]);
-                }
+                for (int f = 0; f < NSTG; ++f)
+                    if (f >= f_lo && f < f_hi) {
+                        const double* src = field(f) + (size_t)line_first * g.LD + ybase;
+                        double* d = dst + (f - f_lo) * FS + slot_first * PITCH;
+                        for (int k = 0; k < nlines; ++k) bulk_g2s(d + k * PITCH, src + (size_t)k * g.LD, line_bytes, bp);
+                    }
             }
         }
         __syncwarp();
     };
+    auto issue = [&](int buf, int line_first, int nlines, int slot_first) {
+        issue_fields(sS + buf * STAGE, &bar[buf], 0, NBUF, line_first, nlines, slot_first);
+    };
+    auto issue_U = [&](int line_first, int nlines, int slot_first) {
+        issue_fields(sU1, &bar[2], NF, NF + 1, line_first, nlines, slot_first);
+    };
+    auto issue_V = [&](int line_first, int nlines, int slot_first) {
+        issue_fields(sV1, &bar[3], NF + 1, NF + 2, line_first, nlines, slot_first);
+    };
+    uint32_t phU = 0, phV = 0;
 
     double a0[NC][NF], U0[NC], xc[NC][NOUT], yc[NC][NACC];
 #pragma unroll
@@ -760,6 +796,10 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         const int ix = m0 * P;
         if (m0 > 0) issue(1, ix - P + 1, P, 0);   // lines (m0-1)P+1 .. m0*P -> slots 0 .. P-1
         else issue(1, 0, 1, P - 1);               // line 0 -> slot P-1 (the other slots hold stale values, results unused)
+        if constexpr (SPLIT) {
+            if (m0 > 0) { issue_V(ix - P + 1, P, 0); issue_U(ix - P + 1, P, 0); }
+            else { issue_V(0, 1, P - 1); issue_U(0, 1, P - 1); }
+        }
         issue(0, ix + 1, P, 0);                   // first marching step
         if (xthr && m0 > 0) {
 #pragma unroll
@@ -773,12 +813,18 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
 #pragma unroll
         for (int l = 0; l < NL; ++l) wx[l] = 0.5 * g.dx * asm_weight<P>(ix - P + 1 + sp + l * G, g.nex);
         mbar_wait(&bar[1], 0);
+        if constexpr (SPLIT) { mbar_wait(&bar[3], phV); phV ^= 1; }
         const double* sB = sS + STAGE;
-        M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, 0);
+        M3::yphase(nty, halo, wx, cc, ky, sB, sV1, sA, sT, 0);
         __syncwarp();
+        if constexpr (SPLIT) {
+            issue_V(ix + 1, P, 0);                // V of the first marching step: the single V stage is free again
+            mbar_wait(&bar[2], phU);
+            phU ^= 1;
+        }
         if (xthr) {
             if (m0 > 0) {
-                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, 0);
+                M3::template xphase<false>(g, A, m0 - 1, iy0, c0, topi, own, colflag, sB, sU1, sA, sT, wyA, cc, a0, U0, xc, yc, pd, 0);
             } else {
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
@@ -787,7 +833,7 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
                     for (int c = 0; c < NC; ++c) a0[c][f] = v.v[c];
                 }
                 if constexpr (M3::NV) {
-                    const VecN<NC> v = ld_vec<NC>(sB + NF * FS + (P - 1) * PITCH + c0);
+                    const VecN<NC> v = ld_vec<NC>((SPLIT ? sU1 : sB + NF * FS) + (P - 1) * PITCH + c0);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) U0[c] = v.v[c];
                 }
@@ -801,6 +847,7 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
             }
         }
         __syncwarp();   // buffer 1 and the accumulators are free again
+        if constexpr (SPLIT) issue_U(ix + 1, P, 0);
         if (m0 + 1 < m1) issue(1, (m0 + 1) * P + 1, P, 0);
     }
 
@@ -837,10 +884,19 @@ __global__ void __launch_bounds__(32) sem_march3_kernel(const __grid_constant__ 
         // z == 0 (m < 2^30), but the compiler cannot prove it: uniform and different in every trip, so the constant-table
         // fetches stay LDCUs next to their DFMAs instead of being hoisted into ~100 registers (and R2UR'd back)
         const int z = (ZIT ? it : m) >> 30;
-        M3::yphase(nty, halo, wx, cc, ky, sB, sA, sT, z);
+        if constexpr (SPLIT) { mbar_wait(&bar[3], phV); phV ^= 1; }
+        M3::yphase(nty, halo, wx, cc, ky, sB, sV1, sA, sT, z);
         __syncwarp();
-        if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
+        if constexpr (SPLIT) {
+            if (m + 1 < m1) issue_V((m + 1) * P + 1, P, 0);   // the V stage is free: the x phase of this step hides the refill
+            mbar_wait(&bar[2], phU);
+            phU ^= 1;
+        }
+        if (xthr) M3::template xphase<true>(g, A, m, iy0, c0, topi, own, colflag, sB, sU1, sA, sT, wyA, cc, a0, U0, xc, yc, pd, z);
         __syncwarp();   // buffer b and the accumulators are free: refill the buffer with the lines of step m + 2
+        if constexpr (SPLIT) {
+            if (m + 1 < m1) issue_U((m + 1) * P + 1, P, 0);   // the U stage is free: the y phase of the next step hides the refill
+        }
         if (m + 2 < m1) issue(b, (m + 2) * P + 1, P, 0);
     }
 
