@@ -95,3 +95,116 @@ def test_single_slot_would_not_be_enough():
     assert unread == (0, 1) and unread[1] > b.consumed             # rank 1 still needs this line ...
     b.slot[0][0] = (0, 2); b.arrived[0] = 2; a.sent = 2            # ... and rank 0 pushes epoch 2: parity 0, another slot
     assert b.slot[0][1] == (0, 1)                                  # untouched; with one slot it would now hold (0, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The one-launch partitioned apply (sem_march3_kernel<.., XCH = true>, sem_capi.cu::fused_apply): the exchange happens INSIDE
+# the operator kernel, per strip.  Model: a launch is a list of one-warp CTAs dispatched in order into `slots` resident
+# places -- first the edge CTAs (left edge strips, then right edge strips), then interior CTAs that only do work.  An edge CTA
+# of strip s on side d: march (a few work steps), PUSH its segment into the neighbour's slot[d'][s][e & 1] and release the
+# neighbour's arrived[d'][s] = e, then WAIT for its own arrived[d][s] >= e, read slot[d][s][e & 1], set epoch[d][s] = e and
+# retire.  A waiting CTA keeps its slot.  Launch e + 1 of a rank starts when every CTA of its launch e has retired (stream
+# order).  Claims checked under random interleavings: no deadlock when the 2 x strips edge CTAs fit the resident slots; every
+# read returns the neighbour's segment of the SAME epoch; a slot is never overwritten before it was read (two parities suffice).
+class FusedRank:
+    def __init__(self, r, world, strips):
+        self.r = r
+        self.sides = [d for d, n in ((0, r - 1), (1, r + 1)) if 0 <= n < world]     # 0: left line, 1: right line
+        self.nb = {0: r - 1, 1: r + 1}
+        self.slot = {d: [[None, None] for _ in range(strips)] for d in self.sides}
+        self.arrived = {d: [0] * strips for d in self.sides}
+        self.epoch = {d: [0] * strips for d in self.sides}
+        self.launch = 0
+        self.pending, self.resident = [], []
+
+
+def run_fused(world, strips, slots, interior, launches, seed, bias=None, other_path=None):
+    rng = random.Random(seed)
+    ranks = [FusedRank(r, world, strips) for r in range(world)]
+
+    def start_launch(k):
+        k.launch += 1
+        k.pending = [["edge", d, s, rng.randint(1, 3), "march"] for d in k.sides for s in range(strips)]
+        k.pending += [["interior", None, None, rng.randint(2, 6), "march"] for _ in range(interior)]
+        k.resident = []
+
+    for k in ranks:
+        start_launch(k)
+    steps, lead = 0, 0
+    while any(k.launch <= launches for k in ranks):
+        steps += 1
+        assert steps < 5_000_000, "deadlock"
+        order = [r for r in range(world) if ranks[r].launch <= launches]
+        rng.shuffle(order)
+        if bias is not None and bias in order and rng.random() < 0.9:
+            order.remove(bias)
+            order.insert(0, bias)
+        progressed = False
+        for r in order:
+            k = ranks[r]
+            while k.pending and len(k.resident) < slots:          # the hardware scheduler: in launch order
+                k.resident.append(k.pending.pop(0))
+            if not k.resident:                                     # launch complete
+                if k.launch == launches:
+                    k.launch += 1                                  # done
+                else:
+                    start_launch(k)
+                progressed = True
+                break
+            cands = list(range(len(k.resident)))
+            rng.shuffle(cands)
+            for i in cands:
+                cta = k.resident[i]
+                kind, d, s, work, pc = cta
+                e = k.launch
+                if pc == "march":
+                    cta[3] -= 1
+                    if cta[3] <= 0:
+                        cta[4] = "push" if kind == "edge" else "done"
+                elif pc == "push" and r == other_path:
+                    cta[4] = "wait"                                # this rank is on the other protocol: writes other flags
+                elif pc == "push":
+                    peer, dp = ranks[k.nb[d]], 1 - d
+                    old = peer.slot[dp][s][e & 1]
+                    assert old is None or old[1] <= peer.epoch[dp][s], f"rank {r} overwrites an unread segment: {old}"
+                    peer.slot[dp][s][e & 1] = (r, e, s)
+                    peer.arrived[dp][s] = e
+                    cta[4] = "wait"
+                elif pc == "wait":
+                    if k.arrived[d][s] < e:
+                        continue                                   # spinning: holds its slot, try another CTA
+                    lead = max(lead, k.arrived[d][s] - e)
+                    assert k.slot[d][s][e & 1] == (k.nb[d], e, s), (r, d, s, e, k.slot[d][s])
+                    k.epoch[d][s] = e
+                    cta[4] = "done"
+                if cta[4] == "done":
+                    k.resident.pop(i)
+                progressed = True
+                break
+            if progressed:
+                break
+        assert progressed, "no CTA of any rank can make progress: deadlock"
+    return lead
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_in_kernel_exchange_protocol(world):
+    lead = 0
+    for seed in range(12):
+        # edge CTAs co-resident (what fused_apply_possible requires: 4 x strips <= resident slots)
+        lead = max(lead, run_fused(world, strips=5, slots=20, interior=30, launches=12, seed=seed))
+        for bias in (0, world - 1, world // 2):
+            lead = max(lead, run_fused(world, strips=5, slots=20, interior=30, launches=12, seed=100 * seed + bias, bias=bias))
+        # the tightest co-resident case: exactly the edge CTAs of a middle rank fit
+        lead = max(lead, run_fused(world, strips=4, slots=8, interior=10, launches=8, seed=7000 + seed, bias=seed % world))
+    assert lead <= 1
+
+
+def test_in_kernel_exchange_needs_the_same_path_on_both_sides():
+    """The world-3 bug of round 2: the choice between the one-launch exchange and the exchange kernels used per-rank numbers, so
+    a rank with a narrow slab took the other path (other mailbox region, other flags) and both sides spun on flags the
+    neighbour never writes.  In the model a rank that does not write the one-launch flags starves its neighbours' waiting
+    edge CTAs: no CTA can make progress.  (The real kernel ends in its 120 s trap; the choice now only uses numbers all ranks
+    agreed on at attach time, sem_capi.cu::fused_apply_possible.)"""
+    with pytest.raises(AssertionError, match="deadlock"):
+        run_fused(3, strips=3, slots=12, interior=4, launches=2, seed=1, other_path=1)
