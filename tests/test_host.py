@@ -195,3 +195,50 @@ def test_assemble_matrix_and_tensor_element_arrays():
     assert abs(K - Ko).max() < 1e-12
     with pytest.raises(ValueError):
         SEM.assemble(np.zeros((2, 2, 3)))
+
+
+def test_public_signatures_match_the_reference():
+    """Drop-in boundary: every public function / method of the reference's hot-path modules (tests/golden/api_signatures.json,
+    recorded from /root/reference with `ast` by tests/golden/make_api_signatures.py) exists here with the same parameter names in
+    the same order and the same defaults; the drop-in may only append keyword parameters (device, partition, precond ...)."""
+    import ast
+    import inspect
+    import json
+    import sem_b200
+    from sem_b200 import GLL, SEM, Boussinesq_SequentialCoupler
+    api = json.load(open(os.path.join(ROOT, "tests", "golden", "api_signatures.json")))
+    homes = {"ConvectionDiffusion_Solver": sem_b200, "NavierStokes_Solver": sem_b200, "SEM": SEM, "GLL": GLL,
+             "Boussinesq_SequentialCoupler": Boussinesq_SequentialCoupler}
+
+    def same_default(ref_src, got):
+        if ref_src is None:
+            return got is inspect.Parameter.empty
+        if got is inspect.Parameter.empty:
+            return False
+        try:
+            return ast.literal_eval(ref_src) == got
+        except (ValueError, SyntaxError):
+            return True                           # a non-literal default of the reference (none on this path today)
+
+    missing, wrong = [], []
+    for mod, entry in api.items():
+        home = homes[mod]
+        items = [(f"{mod}.{n}", getattr(home, n, None), ps) for n, ps in entry["functions"].items()]
+        for cname, methods in entry["classes"].items():
+            cls = getattr(home, cname, None)
+            items += [(f"{cname}.{n}", getattr(cls, n, None) if cls else None, ps) for n, ps in methods.items()]
+        for name, obj, ref_params in items:
+            if obj is None:
+                missing.append(name)
+                continue
+            got = list(inspect.signature(obj).parameters.values())
+            for i, rp in enumerate(ref_params):
+                if i >= len(got) or got[i].name != rp["name"] or not same_default(rp["default"], got[i].default):
+                    wrong.append(f"{name}: parameter {i} is {got[i] if i < len(got) else None}, reference {rp}")
+                    break
+            else:
+                extra = got[len(ref_params):]
+                if any(p.default is inspect.Parameter.empty and p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL) for p in extra):
+                    wrong.append(f"{name}: extra parameters without defaults {extra}")
+    assert not missing, f"missing: {missing}"
+    assert not wrong, "\n".join(wrong)
